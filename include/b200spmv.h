@@ -1,0 +1,151 @@
+/*
+ * b200spmv.h -- C-ABI of the B200-native SpMV engine (libb200spmv.so).
+ *
+ * This is the drop-in boundary for the hot path of hir0shim/singleSpMV: the per-format
+ * plugin pair
+ *
+ *     void OptimizeProblem(const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_opt);
+ *     extern "C" void SpMV(const SpMatOpt &A, const VecOpt &x, Vec &y);
+ *
+ * declared in /root/reference/src/opt_{crs,coo,ell,jds,dia,ss,css}.h (e.g. opt_crs.h:15-18)
+ * and selected at compile time by /root/reference/src/opt.h:1-28 / opt.cpp:5-33.
+ * A maintainer of the reference binds these entry points from a plugin file
+ * (singlespmv_b200/plugin/opt_b200.{h,cpp}; INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C types only; `_h` = host pointer, `_d` = device pointer on the current device
+ *   - indices are int32 and values fp64, like the reference (src/param.h:1-7, src/util.h:7-19)
+ *   - input is COO sorted by (row, col) without duplicate coordinates (src/util.cpp:51)
+ *   - every function returns 0 on success or a negative b200spmv_status; it never exits
+ *     (the reference's plugins assert()/exit(): src/util.h:48-55, src/util.cpp:32-35)
+ *   - a handle is used from one host thread at a time
+ *   - there is NO CPU fallback: without a CUDA device every compute entry fails with
+ *     B200SPMV_ERR_CUDA.
+ */
+#ifndef B200SPMV_H
+#define B200SPMV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPMV_VERSION 100
+#if defined(__GNUC__)
+#define B200SPMV_API __attribute__((visibility("default")))
+#else
+#define B200SPMV_API
+#endif
+
+typedef struct b200spmv_matrix b200spmv_matrix;      /* opaque converted matrix (SpMatOpt) */
+
+/* Storage formats = the reference's plugins (src/opt.h:1-28) + the vendored CSR5
+ * (opt/Benchmark_SpMV_using_CSR5/CSR5_cuda/anonymouslib_cuda.h). */
+typedef enum {
+    B200SPMV_CRS  = 0,   /* src/opt_crs.cpp  */
+    B200SPMV_COO  = 1,   /* src/opt_coo.cpp  */
+    B200SPMV_ELL  = 2,   /* src/opt_ell.cpp  (device layout: sliced ELL) */
+    B200SPMV_JDS  = 3,   /* src/opt_jds.cpp  */
+    B200SPMV_DIA  = 4,   /* src/opt_dia.cpp  */
+    B200SPMV_SS   = 5,   /* src/opt_ss.cpp   */
+    B200SPMV_CSS  = 6,   /* src/opt_css.cpp  */
+    B200SPMV_CSR5 = 7    /* opt/.../CSR5_cuda */
+} b200spmv_format;
+
+typedef enum {
+    B200SPMV_OK              =  0,
+    B200SPMV_ERR_INVALID     = -1,   /* bad argument / input breaks the contract above   */
+    B200SPMV_ERR_CUDA        = -2,   /* CUDA runtime error (see b200spmv_last_error)      */
+    B200SPMV_ERR_UNSUPPORTED = -3,   /* format/option combination not available           */
+    B200SPMV_ERR_STATE       = -4,   /* call order (multiply before convert, ...)         */
+    B200SPMV_ERR_NOMEM       = -5
+} b200spmv_status;
+
+/* Tunables.  The reference fixes these at compile time with -D macros
+ * (Makefile:10-21, src/param.h:9-20); here they are per-handle.  Zero = default. */
+typedef struct {
+    int segment_width;   /* SS/CSS: SEGMENT_WIDTH (W), power of two; default 4 (= ALIGNMENT/8, ALIGNMENT=32) */
+    int n_block;         /* CSS: N_BLOCK; default 1 */
+    int csr5_sigma;      /* CSR5: sigma; 0 = auto (anonymouslib_cuda.h:293-317) */
+    int ss_faithful;     /* SS/CSS: 1 = three-phase Mul/fold/gather with val_buf, the reference's
+                            operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
+    int reserved[12];
+} b200spmv_options;
+
+/* ---- library ---- */
+B200SPMV_API int b200spmv_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+B200SPMV_API const char *b200spmv_last_error(void);
+B200SPMV_API int b200spmv_device_count(int *count);
+
+/* ---- lifetime (the reference never frees: src/util.h:12-18) ---- */
+B200SPMV_API int b200spmv_create(int format, const b200spmv_options *opts /* may be NULL */, b200spmv_matrix **out);
+B200SPMV_API int b200spmv_destroy(b200spmv_matrix *m);
+
+/* ---- conversion: replaces OptimizeProblem (src/opt_crs.cpp:10, opt_ell.cpp:7, opt_jds.cpp:8,
+ * opt_dia.cpp:6, opt_ss.cpp:14, opt_css.cpp:17, opt_coo.cpp:3).  All format arrays are built on
+ * the device from the COO triplets.  _host copies the triplets H2D first. */
+B200SPMV_API int b200spmv_convert_coo_host(b200spmv_matrix *m, int nRow, int nCol, long long nnz,
+                              const int *row_h, const int *col_h, const double *val_h);
+B200SPMV_API int b200spmv_convert_coo_device(b200spmv_matrix *m, int nRow, int nCol, long long nnz,
+                                const int *row_d, const int *col_d, const double *val_d,
+                                void *stream /* cudaStream_t */);
+/* JDS only, optional, before convert: impose the row permutation (e.g. the one libstdc++'s
+ * unstable std::sort produced for the reference, src/opt_jds.cpp:41-46).  It must order rows
+ * by non-increasing length.  Without it ties are ordered by ascending row. */
+B200SPMV_API int b200spmv_jds_set_perm_host(b200spmv_matrix *m, const int *perm_h, int nRow);
+
+/* ---- multiply: replaces SpMV (src/opt_crs.cpp:45 etc.).  y := A*x, every y[0..nRow) is
+ * overwritten (beta = 0); the call may be repeated any number of times (src/main.cpp:41-88). */
+B200SPMV_API int b200spmv_multiply(b200spmv_matrix *m, const double *x_d, double *y_d, void *stream);
+/* Host semantics (what SpMV(A_opt, x_opt, y) means to the reference's driver): copies x H2D,
+ * multiplies, copies y D2H, synchronises -- like src/opt_cusparse.cpp:72-82. */
+B200SPMV_API int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h);
+/* Rows [rowBegin,rowEnd) only (CRS): used by the row-partitioned multi-GPU path to overlap the
+ * interior block with the halo exchange. */
+B200SPMV_API int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const double *x_d,
+                           double *y_d, void *stream);
+
+/* ---- read-back for parity checks: the SpMatOpt fields under the reference's names.
+ * Scalars: nRow nCol nNnz | K | maxLength | nDiag | H nStep W | B nBlock totalH | sigma p ... and
+ *          alg_bytes (compulsory bytes per multiply), launches (kernels/multiply).
+ * Arrays are returned in the reference's LOGICAL layout (ELL [nRow][K], DIA [nDiag][nCol], ...).
+ * get_array: dst_h == NULL returns the size in bytes; otherwise copies and returns the size;
+ * negative = error. */
+B200SPMV_API int b200spmv_get_scalar(b200spmv_matrix *m, const char *name, long long *out);
+B200SPMV_API long long b200spmv_get_array(b200spmv_matrix *m, const char *name, void *dst_h, long long dst_bytes);
+
+/* ---- synthetic inputs on the device (same definitions as oracle/synth_oracle.c).
+ * The reference loads Matrix-Market text (src/util.cpp:30-66); BASELINE.json's shapes are up to
+ * 938 M non-zeros, so they are generated in HBM instead. */
+typedef enum {
+    B200SPMV_SYNTH_LAP2D5  = 0,  /* p0 = n        : 2-D 5-point Laplacian, n*n rows          */
+    B200SPMV_SYNTH_LAP3D7  = 1,  /* p0 = n        : 3-D 7-point Laplacian, n^3 rows          */
+    B200SPMV_SYNTH_BOX3D27 = 2,  /* p0 = n        : 3-D 27-point stencil,  n^3 rows          */
+    B200SPMV_SYNTH_UNIFORM = 3,  /* p0 = nRow=nCol, p1 = K distinct uniform columns per row  */
+    B200SPMV_SYNTH_RMAT    = 4   /* p0 = scale, p1 = edge draws; duplicates removed          */
+} b200spmv_synth_kind;
+
+typedef struct {
+    int nRow, nCol;          /* GLOBAL dimensions                                             */
+    int rowBegin, rowEnd;    /* rows actually generated (row ids in row_d stay global)        */
+    long long nnz;           /* entries in the arrays                                         */
+    int *row_d, *col_d;
+    double *val_d;
+} b200spmv_coo;
+
+/* Generates rows [rowBegin,rowEnd) (rowEnd <= 0: all rows) of the named matrix into newly
+ * allocated device arrays.  RMAT supports the full range only. */
+B200SPMV_API int b200spmv_synth(int kind, long long p0, long long p1, unsigned long long seed,
+                   int rowBegin, int rowEnd, b200spmv_coo *out, void *stream);
+B200SPMV_API int b200spmv_coo_free(b200spmv_coo *coo);
+/* Copies the triplets to host arrays of coo->nnz entries (parity checks, CPU baseline input). */
+B200SPMV_API int b200spmv_coo_download(const b200spmv_coo *coo, int *row_h, int *col_h, double *val_h);
+
+/* x = rand()/RAND_MAX stream of src/util.cpp:92-102 after srand(seed) (src/main.cpp:18):
+ * writes x_h[0..nCol) (and y_h[0..nRow) if y_h != NULL), host side, glibc rand(). */
+B200SPMV_API int b200spmv_reference_vectors(unsigned seed, int nCol, int nRow, double *x_h, double *y_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPMV_H */

@@ -74,6 +74,36 @@ ORC_API long long synth_stencil(int kind, int n, int *row, int *col, double *val
     return at;
 }
 
+/* Rows [rowBegin, rowEnd) of the same stencil matrices (row ids stay global): what one rank of the
+ * row-partitioned multi-GPU path owns, and the bounded CPU-baseline sample of bench.py.
+ * The caller sizes the arrays for (rowEnd-rowBegin) * {5,7,27} entries.  Returns the count. */
+ORC_API long long synth_stencil_range(int kind, int n, int rowBegin, int rowEnd, int *row, int *col, double *val)
+{
+    long long at = 0;
+    for (int r = rowBegin; r < rowEnd; r++) {
+        if (kind == 0) {
+            int i = r / n, j = r % n;
+            for (int di = -1; di <= 1; di++) for (int dj = -1; dj <= 1; dj++) {
+                if (di != 0 && dj != 0) continue;
+                int ii = i + di, jj = j + dj;
+                if (ii < 0 || ii >= n || jj < 0 || jj >= n) continue;
+                row[at] = r; col[at] = ii * n + jj; val[at] = (di == 0 && dj == 0) ? 4.0 : -1.0; at++;
+            }
+            continue;
+        }
+        int k = r % n, j = (r / n) % n, i = r / (n * n);
+        for (int di = -1; di <= 1; di++) for (int dj = -1; dj <= 1; dj++) for (int dk = -1; dk <= 1; dk++) {
+            int taxi = abs(di) + abs(dj) + abs(dk);
+            if (kind == 1 && taxi > 1) continue;
+            int ii = i + di, jj = j + dj, kk = k + dk;
+            if (ii < 0 || ii >= n || jj < 0 || jj >= n || kk < 0 || kk >= n) continue;
+            row[at] = r; col[at] = (ii * n + jj) * n + kk;
+            val[at] = taxi == 0 ? (kind == 1 ? 6.0 : 26.0) : -1.0; at++;
+        }
+    }
+    return at;
+}
+
 /* ---- uniform random: every row has exactly K distinct columns.  Row r draws candidates
  * c_j = mix64(rowkey + j) mod nCol, j = 0,1,2,..., keeping the first K distinct ones, then
  * sorts them.  Rows [rowBegin, rowEnd) are written (row ids stay global). */

@@ -1,0 +1,229 @@
+// api.cu -- the extern "C" surface declared in include/b200spmv.h.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace b2 {
+const char *last_error_cstr();
+}
+using namespace b2;
+
+struct b200spmv_matrix {
+    int format = 0;
+    b200spmv_options opt{};
+    std::unique_ptr<Format> impl;
+    bool converted = false;
+    // staging for host-semantics multiply
+    DevBuf<double> x_stage, y_stage;
+    cudaStream_t stream = nullptr;
+    ~b200spmv_matrix()
+    {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static Format *make_format(int format, const b200spmv_options &o)
+{
+    switch (format) {
+    case B200SPMV_CRS: return make_crs(o);
+    case B200SPMV_COO: return make_coo(o);
+    case B200SPMV_ELL: return make_ell(o);
+    case B200SPMV_JDS: return make_jds(o);
+    case B200SPMV_DIA: return make_dia(o);
+    case B200SPMV_SS: return make_ss(o);
+    case B200SPMV_CSS: return make_css(o);
+    case B200SPMV_CSR5: return make_csr5(o);
+    default: return nullptr;
+    }
+}
+
+static int require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libb200spmv has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return B200SPMV_ERR_CUDA;
+    }
+    return B200SPMV_OK;
+}
+
+extern "C" {
+
+int b200spmv_version(void) { return B200SPMV_VERSION; }
+
+const char *b200spmv_last_error(void) { return last_error_cstr(); }
+
+int b200spmv_device_count(int *count)
+{
+    if (!count) return B200SPMV_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return B200SPMV_OK;
+}
+
+int b200spmv_create(int format, const b200spmv_options *opts, b200spmv_matrix **out)
+{
+    clear_error();
+    if (!out) {
+        set_error("create: out is NULL");
+        return B200SPMV_ERR_INVALID;
+    }
+    *out = nullptr;
+    b200spmv_options o{};
+    if (opts) o = *opts;
+    if (o.segment_width == 0) o.segment_width = 4;     // ALIGNMENT/sizeof(double), param.h:9-11 with ALIGNMENT=32
+    if (o.n_block == 0) o.n_block = 1;                 // param.h:18-20
+    if (o.segment_width < 1 || (o.segment_width & (o.segment_width - 1))) {
+        set_error("create: segment_width=%d must be a power of two (reference src/opt_ss.cpp:272 masks with W-1)", o.segment_width);
+        return B200SPMV_ERR_INVALID;
+    }
+    if (o.n_block < 1 || o.csr5_sigma < 0 || o.csr5_sigma > 32) {
+        set_error("create: bad option (n_block=%d csr5_sigma=%d)", o.n_block, o.csr5_sigma);
+        return B200SPMV_ERR_INVALID;
+    }
+    Format *f = make_format(format, o);
+    if (!f) {
+        set_error("create: unknown format %d", format);
+        return B200SPMV_ERR_INVALID;
+    }
+    b200spmv_matrix *m = new b200spmv_matrix();
+    m->format = format;
+    m->opt = o;
+    m->impl.reset(f);
+    *out = m;
+    return B200SPMV_OK;
+}
+
+int b200spmv_destroy(b200spmv_matrix *m)
+{
+    delete m;
+    return B200SPMV_OK;
+}
+
+int b200spmv_convert_coo_device(b200spmv_matrix *m, int nRow, int nCol, long long nnz, const int *row_d,
+                                const int *col_d, const double *val_d, void *stream)
+{
+    clear_error();
+    if (!m) { set_error("convert: NULL handle"); return B200SPMV_ERR_INVALID; }
+    if (nRow < 0 || nCol < 0 || nnz < 0 || nnz > 0x7fffffffLL) {
+        set_error("convert: dimensions out of int32 range (nRow=%d nCol=%d nnz=%lld); the reference is int32 too (src/util.h:8)", nRow, nCol, nnz);
+        return B200SPMV_ERR_INVALID;
+    }
+    if (nnz > 0 && (!row_d || !col_d || !val_d)) { set_error("convert: NULL COO array"); return B200SPMV_ERR_INVALID; }
+    B2_TRY(require_device());
+    CooView A{nRow, nCol, (int)nnz, row_d, col_d, val_d};
+    m->converted = false;
+    int st = m->impl->convert(A, (cudaStream_t)stream);
+    if (st == B200SPMV_OK) m->converted = true;
+    return st;
+}
+
+int b200spmv_convert_coo_host(b200spmv_matrix *m, int nRow, int nCol, long long nnz, const int *row_h,
+                              const int *col_h, const double *val_h)
+{
+    clear_error();
+    if (!m) { set_error("convert: NULL handle"); return B200SPMV_ERR_INVALID; }
+    if (nnz < 0 || nnz > 0x7fffffffLL) { set_error("convert: nnz=%lld out of int32 range", nnz); return B200SPMV_ERR_INVALID; }
+    if (nnz > 0 && (!row_h || !col_h || !val_h)) { set_error("convert: NULL COO array"); return B200SPMV_ERR_INVALID; }
+    B2_TRY(require_device());
+    DevBuf<int> r, c;
+    DevBuf<double> v;
+    B2_TRY(r.alloc((size_t)nnz));
+    B2_TRY(c.alloc((size_t)nnz));
+    B2_TRY(v.alloc((size_t)nnz));
+    if (nnz) {
+        B2_CUDA(cudaMemcpy(r.p, row_h, r.bytes(), cudaMemcpyHostToDevice));
+        B2_CUDA(cudaMemcpy(c.p, col_h, c.bytes(), cudaMemcpyHostToDevice));
+        B2_CUDA(cudaMemcpy(v.p, val_h, v.bytes(), cudaMemcpyHostToDevice));
+    }
+    return b200spmv_convert_coo_device(m, nRow, nCol, nnz, r.p, c.p, v.p, nullptr);
+}
+
+int b200spmv_jds_set_perm_host(b200spmv_matrix *m, const int *perm_h, int nRow)
+{
+    clear_error();
+    if (!m || !perm_h) { set_error("jds_set_perm: NULL argument"); return B200SPMV_ERR_INVALID; }
+    return m->impl->set_perm(perm_h, nRow);
+}
+
+static int check_ready(b200spmv_matrix *m, const void *x, const void *y)
+{
+    if (!m) { set_error("multiply: NULL handle"); return B200SPMV_ERR_INVALID; }
+    if (!m->converted) { set_error("multiply: matrix not converted yet"); return B200SPMV_ERR_STATE; }
+    if ((!x && m->impl->nCol > 0) || (!y && m->impl->nRow > 0)) { set_error("multiply: NULL vector"); return B200SPMV_ERR_INVALID; }
+    return B200SPMV_OK;
+}
+
+int b200spmv_multiply(b200spmv_matrix *m, const double *x_d, double *y_d, void *stream)
+{
+    B2_TRY(check_ready(m, x_d, y_d));
+    return m->impl->multiply(x_d, y_d, (cudaStream_t)stream);
+}
+
+int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const double *x_d, double *y_d,
+                           void *stream)
+{
+    B2_TRY(check_ready(m, x_d, y_d));
+    return m->impl->multiply_rows(rowBegin, rowEnd, x_d, y_d, (cudaStream_t)stream);
+}
+
+int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
+{
+    B2_TRY(check_ready(m, x_h, y_h));
+    Format *f = m->impl.get();
+    if (!m->stream) B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (m->x_stage.n != (size_t)f->nCol) B2_TRY(m->x_stage.alloc((size_t)f->nCol));
+    if (m->y_stage.n != (size_t)f->nRow) B2_TRY(m->y_stage.alloc((size_t)f->nRow));
+    B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
+    B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
+    B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
+    B2_CUDA(cudaStreamSynchronize(m->stream));
+    return B200SPMV_OK;
+}
+
+int b200spmv_get_scalar(b200spmv_matrix *m, const char *name, long long *out)
+{
+    if (!m || !name || !out) { set_error("get_scalar: NULL argument"); return B200SPMV_ERR_INVALID; }
+    if (!m->converted) { set_error("get_scalar: matrix not converted yet"); return B200SPMV_ERR_STATE; }
+    std::string n(name);
+    Format *f = m->impl.get();
+    if (n == "nRow") { *out = f->nRow; return B200SPMV_OK; }
+    if (n == "nCol") { *out = f->nCol; return B200SPMV_OK; }
+    if (n == "nNnz") { *out = f->nnz; return B200SPMV_OK; }
+    if (n == "format") { *out = m->format; return B200SPMV_OK; }
+    if (f->scalar(n, out)) return B200SPMV_OK;
+    set_error("get_scalar: format %d has no scalar '%s'", m->format, name);
+    return B200SPMV_ERR_INVALID;
+}
+
+long long b200spmv_get_array(b200spmv_matrix *m, const char *name, void *dst_h, long long dst_bytes)
+{
+    if (!m || !name) { set_error("get_array: NULL argument"); return B200SPMV_ERR_INVALID; }
+    if (!m->converted) { set_error("get_array: matrix not converted yet"); return B200SPMV_ERR_STATE; }
+    long long r = m->impl->array(std::string(name), dst_h, dst_bytes);
+    if (r == -1000) {
+        set_error("get_array: format %d has no array '%s'", m->format, name);
+        return B200SPMV_ERR_INVALID;
+    }
+    return r;
+}
+
+int b200spmv_reference_vectors(unsigned seed, int nCol, int nRow, double *x_h, double *y_h)
+{
+    if (nCol > 0 && !x_h) { set_error("reference_vectors: NULL x"); return B200SPMV_ERR_INVALID; }
+    srand(seed);                                                     // src/main.cpp:18
+    for (int i = 0; i < nCol; i++) x_h[i] = double(rand()) / RAND_MAX;   // src/util.cpp:97-99
+    if (y_h)
+        for (int i = 0; i < nRow; i++) y_h[i] = double(rand()) / RAND_MAX;
+    return B200SPMV_OK;
+}
+
+}  // extern "C"

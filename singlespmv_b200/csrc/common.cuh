@@ -1,0 +1,188 @@
+// common.cuh -- shared host/device plumbing of libb200spmv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b200spmv.h"
+
+namespace b2 {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+void clear_error();
+
+#define B2_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            b2::set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return B200SPMV_ERR_CUDA;                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define B2_TRY(expr)                       \
+    do {                                   \
+        int s__ = (expr);                  \
+        if (s__ != B200SPMV_OK) return s__; \
+    } while (0)
+
+#define B2_KERNEL_CHECK() B2_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------- device memory
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) count = 1;   // keep pointers non-null so kernels can take them
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            n = 0;
+            set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? B200SPMV_ERR_NOMEM : B200SPMV_ERR_CUDA;
+        }
+        return B200SPMV_OK;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// Copies a device array to a host destination with the get_array() size protocol.
+long long export_device(const void *src_d, size_t bytes, void *dst_h, long long dst_bytes);
+long long export_host(const void *src_h, size_t bytes, void *dst_h, long long dst_bytes);
+
+// ---------------------------------------------------------------- input view + format interface
+struct CooView {
+    int nRow, nCol;
+    int nnz;                 // < 2^31 like the reference (src/util.h:8)
+    const int *row, *col;    // device
+    const double *val;       // device
+};
+
+struct Format {
+    int nRow = 0, nCol = 0, nnz = 0;
+    virtual ~Format() {}
+    virtual int convert(const CooView &A, cudaStream_t s) = 0;
+    virtual int multiply(const double *x, double *y, cudaStream_t s) = 0;
+    virtual int multiply_rows(int, int, const double *, double *, cudaStream_t)
+    {
+        set_error("multiply_rows: only the CRS format supports row ranges");
+        return B200SPMV_ERR_UNSUPPORTED;
+    }
+    // format-specific scalars/arrays; return false / -1 when the name is unknown
+    virtual bool scalar(const std::string &name, long long *out) = 0;
+    virtual long long array(const std::string &name, void *dst_h, long long dst_bytes) = 0;
+    virtual int set_perm(const int *, int)
+    {
+        set_error("set_perm: only the JDS format takes a row permutation");
+        return B200SPMV_ERR_UNSUPPORTED;
+    }
+};
+
+Format *make_crs(const b200spmv_options &);
+Format *make_coo(const b200spmv_options &);
+Format *make_ell(const b200spmv_options &);
+Format *make_jds(const b200spmv_options &);
+Format *make_dia(const b200spmv_options &);
+Format *make_ss(const b200spmv_options &);
+Format *make_css(const b200spmv_options &);
+Format *make_csr5(const b200spmv_options &);
+
+// ---------------------------------------------------------------- shared device passes (primitives.cu)
+// ptr[r] = first index i with row[i] >= r, ptr[nRow] = nnz  (reference src/opt_crs.cpp:27-33)
+int build_row_ptr(const int *row_d, int nnz, int nRow, int *ptr_d, cudaStream_t s);
+// max over r of ptr[r+1]-ptr[r]; synchronises the stream
+int max_row_length(const int *ptr_d, int nRow, int *out_h, cudaStream_t s);
+// exclusive prefix sums (CUB); out may alias in; n >= 0
+int exclusive_scan_i32(const int *in_d, int *out_d, int n, cudaStream_t s);
+int exclusive_scan_i64(const long long *in_d, long long *out_d, int n, cudaStream_t s);
+// checks the input contract: sorted by (row, col), no duplicates, indices in range
+int validate_sorted_coo(const CooView &A, cudaStream_t s);
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+// Matrix arrays are read exactly once per multiply: stream them around L1 and mark the lines
+// evict-first in L2 so that they do not push x (the only reused operand) out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_stream_i4(const int *p, uint64_t pol)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream_i2(const int *p, uint64_t pol)
+{
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int ld_stream_i1(const int *p, uint64_t pol)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+                 : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double *p, uint64_t pol)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ld_stream_d1(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+                 : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+// x gathers: cached in L1 (stencil reuse) and kept in L2 with evict-last priority.
+__device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+}  // namespace b2

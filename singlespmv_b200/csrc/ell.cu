@@ -1,0 +1,223 @@
+// ell.cu -- ELL plugin.  Logical content = the reference's ELLPACK (/root/reference/src/opt_ell.cpp:
+// K = longest row :28-31, slot k >= len padded with col = k, val = 0 :46-52, multiply over all K
+// slots :75-89).  Device layout = sliced ELL: slices of 32 rows (one warp), slice-local width
+// rounded to V slots, stored [slice][k/V][lane][V] so that a lane reads V column ids and V
+// values with 128-bit loads and a warp request is one contiguous 512 B / 1 KB run.
+#include "common.cuh"
+
+namespace b2 {
+
+// groups[s] = ceil(max row length in slice s / V)
+template <int V>
+__global__ void ell_slice_groups_kernel(const int *__restrict__ ptr, int nRow, int nSlices,
+                                        long long *__restrict__ groups)
+{
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s > nSlices) return;                       // s == nSlices: sentinel entry for the scan
+    const int r = s * 32 + lane;
+    int len = (s < nSlices && r < nRow) ? ptr[r + 1] - ptr[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) groups[s] = (len + V - 1) / V;
+}
+
+template <int V>
+__global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
+                                const double *__restrict__ val, int nRow, int nSlices,
+                                const long long *__restrict__ slice_off, int *__restrict__ ecol,
+                                double *__restrict__ eval)
+{
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nSlices) return;
+    const int r = s * 32 + lane;
+    const long long g0 = slice_off[s], g1 = slice_off[s + 1];
+    const int b = r < nRow ? ptr[r] : 0, len = r < nRow ? ptr[r + 1] - b : 0;
+    for (long long g = g0; g < g1; g++)
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const int k = (int)(g - g0) * V + j;
+            const size_t at = ((size_t)g * 32 + lane) * V + j;
+            const bool real = k < len;
+            ecol[at] = real ? col[b + k] : (r < nRow ? k : 0);   // padding: col = slot index (opt_ell.cpp:48)
+            eval[at] = real ? val[b + k] : 0.0;
+        }
+}
+
+template <int V> struct EllGroup {
+    int c[V];
+    double v[V];
+};
+
+template <int V>
+__device__ __forceinline__ void ell_load(EllGroup<V> &g, const int *ecol, const double *eval, size_t at,
+                                         uint64_t pol)
+{
+    if (V == 4) {
+        int4 c = ld_stream_i4(ecol + at, pol);
+        double2 a = ld_stream_d2(eval + at, pol), b = ld_stream_d2(eval + at + 2, pol);
+        g.c[0] = c.x; g.c[1] = c.y; g.c[V - 2] = c.z; g.c[V - 1] = c.w;
+        g.v[0] = a.x; g.v[1] = a.y; g.v[V - 2] = b.x; g.v[V - 1] = b.y;
+    } else {
+        int2 c = ld_stream_i2(ecol + at, pol);
+        double2 a = ld_stream_d2(eval + at, pol);
+        g.c[0] = c.x; g.c[1] = c.y;
+        g.v[0] = a.x; g.v[1] = a.y;
+    }
+}
+
+// One lane per row; the K-loop runs in ascending slot order with unfused mul/add, i.e. the
+// reference's own order -> y is bit-identical to opt_ell.cpp / opt_crs.cpp.
+template <int V>
+__global__ void __launch_bounds__(256)
+ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
+                const double *__restrict__ eval, const double *__restrict__ x, double *__restrict__ y,
+                int nRow, int nSlices)
+{
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nSlices) return;
+    const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
+    const long long g0 = slice_off[s], g1 = slice_off[s + 1];
+    double acc = 0.0;
+    long long g = g0;
+    for (; g + 2 <= g1; g += 2) {
+        EllGroup<V> a, b;
+        ell_load<V>(a, ecol, eval, ((size_t)g * 32 + lane) * V, pol_stream);
+        ell_load<V>(b, ecol, eval, ((size_t)(g + 1) * 32 + lane) * V, pol_stream);
+        double xa[V], xb[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) xa[j] = ld_x(x + a.c[j], pol_x);
+#pragma unroll
+        for (int j = 0; j < V; j++) xb[j] = ld_x(x + b.c[j], pol_x);
+#pragma unroll
+        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
+#pragma unroll
+        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xb[j], b.v[j]));
+    }
+    if (g < g1) {
+        EllGroup<V> a;
+        ell_load<V>(a, ecol, eval, ((size_t)g * 32 + lane) * V, pol_stream);
+        double xa[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) xa[j] = ld_x(x + a.c[j], pol_x);
+#pragma unroll
+        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
+    }
+    const int r = s * 32 + lane;
+    if (r < nRow) y[r] = acc;
+}
+
+// Logical [nRow][K] view for parity checks (slots beyond the slice width are padding).
+template <int V>
+__global__ void ell_logical_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
+                                   const double *__restrict__ eval, int nRow, int K, int *__restrict__ lcol,
+                                   double *__restrict__ lval)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nRow * K) return;
+    const int r = (int)(i / K), k = (int)(i % K);
+    const int s = r >> 5, lane = r & 31;
+    const long long g0 = slice_off[s], g1 = slice_off[s + 1];
+    if (k < (int)(g1 - g0) * V) {
+        const size_t at = ((size_t)(g0 + k / V) * 32 + lane) * V + k % V;
+        lcol[i] = ecol[at];
+        lval[i] = eval[at];
+    } else {
+        lcol[i] = k;
+        lval[i] = 0.0;
+    }
+}
+
+struct EllFormat : Format {
+    int K = 0, V = 4, nSlices = 0;
+    long long slots = 0;
+    DevBuf<long long> slice_off;
+    DevBuf<int> ecol;
+    DevBuf<double> eval;
+
+    template <int VV> int convert_t(const CooView &A, const int *ptr, cudaStream_t s)
+    {
+        DevBuf<long long> groups;
+        B2_TRY(groups.alloc((size_t)nSlices + 1));
+        B2_TRY(slice_off.alloc((size_t)nSlices + 1));
+        ell_slice_groups_kernel<VV><<<ceil_div(((long long)nSlices + 1) * 32, 256), 256, 0, s>>>(ptr, nRow, nSlices, groups.p);
+        B2_KERNEL_CHECK();
+        B2_TRY(exclusive_scan_i64(groups.p, slice_off.p, nSlices + 1, s));
+        long long totalGroups = 0;
+        B2_CUDA(cudaMemcpy(&totalGroups, slice_off.p + nSlices, sizeof(long long), cudaMemcpyDeviceToHost));
+        slots = totalGroups * 32 * VV;
+        B2_TRY(ecol.alloc((size_t)slots));
+        B2_TRY(eval.alloc((size_t)slots));
+        if (nSlices) {
+            ell_fill_kernel<VV><<<ceil_div((long long)nSlices * 32, 256), 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices,
+                                                                                      slice_off.p, ecol.p, eval.p);
+            B2_KERNEL_CHECK();
+        }
+        return B200SPMV_OK;
+    }
+
+    int convert(const CooView &A, cudaStream_t s) override
+    {
+        nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
+        B2_TRY(validate_sorted_coo(A, s));
+        DevBuf<int> ptr;
+        B2_TRY(ptr.alloc((size_t)nRow + 1));
+        B2_TRY(build_row_ptr(A.row, nnz, nRow, ptr.p, s));
+        B2_TRY(max_row_length(ptr.p, nRow, &K, s));                 // opt_ell.cpp:28-31
+        if (K > nCol) {
+            set_error("ELL: K=%d exceeds nCol=%d; the reference's padding rule col=k (opt_ell.cpp:48) is undefined", K, nCol);
+            return B200SPMV_ERR_INVALID;
+        }
+        V = (K % 4 == 0 || K >= 32) ? 4 : 2;
+        nSlices = ceil_div(nRow, 32);
+        int st = V == 4 ? convert_t<4>(A, ptr.p, s) : convert_t<2>(A, ptr.p, s);
+        B2_TRY(st);
+        B2_CUDA(cudaStreamSynchronize(s));
+        return B200SPMV_OK;
+    }
+
+    int multiply(const double *x, double *y, cudaStream_t s) override
+    {
+        if (nSlices == 0) return B200SPMV_OK;
+        const int blocks = ceil_div((long long)nSlices * 32, 256);
+        if (V == 4) ell_spmv_kernel<4><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices);
+        else ell_spmv_kernel<2><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices);
+        B2_KERNEL_CHECK();
+        return B200SPMV_OK;
+    }
+
+    bool scalar(const std::string &n, long long *out) override
+    {
+        if (n == "K") { *out = K; return true; }
+        if (n == "slots") { *out = slots; return true; }
+        if (n == "slice_vec") { *out = V; return true; }
+        if (n == "alg_bytes") {   // 12 B per stored slot + slice offsets + x + y
+            *out = 12LL * slots + 8LL * (nSlices + 1) + 8LL * nCol + 8LL * nRow;
+            return true;
+        }
+        if (n == "launches") { *out = 1; return true; }
+        return false;
+    }
+
+    long long array(const std::string &n, void *dst, long long cap) override
+    {
+        if (n != "col_idx" && n != "val") return -1000;
+        const bool isCol = n == "col_idx";
+        const size_t cnt = (size_t)nRow * K, bytes = cnt * (isCol ? sizeof(int) : sizeof(double));
+        if (!dst) return (long long)bytes;
+        DevBuf<int> lcol;
+        DevBuf<double> lval;
+        if (lcol.alloc(cnt) || lval.alloc(cnt)) return B200SPMV_ERR_NOMEM;
+        if (cnt) {
+            if (V == 4) ell_logical_kernel<4><<<ceil_div((long long)cnt, 256), 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
+            else ell_logical_kernel<2><<<ceil_div((long long)cnt, 256), 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
+        }
+        return export_device(isCol ? (const void *)lcol.p : (const void *)lval.p, bytes, dst, cap);
+    }
+};
+
+Format *make_ell(const b200spmv_options &) { return new EllFormat(); }
+
+}  // namespace b2

@@ -1,0 +1,141 @@
+// primitives.cu -- error state and the device passes every conversion is composed of.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace b2 {
+
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+void clear_error() { g_error.clear(); }
+const char *last_error_cstr() { return g_error.c_str(); }
+
+long long export_device(const void *src_d, size_t bytes, void *dst_h, long long dst_bytes)
+{
+    if (!dst_h) return (long long)bytes;
+    if (dst_bytes < (long long)bytes) {
+        set_error("get_array: destination holds %lld bytes, %zu needed", dst_bytes, bytes);
+        return B200SPMV_ERR_INVALID;
+    }
+    if (bytes) {
+        cudaError_t e = cudaMemcpy(dst_h, src_d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("get_array: cudaMemcpy D2H: %s", cudaGetErrorString(e));
+            return B200SPMV_ERR_CUDA;
+        }
+    }
+    return (long long)bytes;
+}
+
+long long export_host(const void *src_h, size_t bytes, void *dst_h, long long dst_bytes)
+{
+    if (!dst_h) return (long long)bytes;
+    if (dst_bytes < (long long)bytes) {
+        set_error("get_array: destination holds %lld bytes, %zu needed", dst_bytes, bytes);
+        return B200SPMV_ERR_INVALID;
+    }
+    if (bytes) memcpy(dst_h, src_h, bytes);
+    return (long long)bytes;
+}
+
+// ---------------------------------------------------------------- row pointer
+// Each ptr entry is written exactly once: entry i fills the rows in (row[i-1], row[i]], the
+// virtual entry i == nnz fills (row[nnz-1], nRow].  Same result as the serial sweep of
+// reference src/opt_crs.cpp:27-33.
+__global__ void row_ptr_kernel(const int *__restrict__ row, int nnz, int nRow, int *__restrict__ ptr)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nnz) return;
+    int prev = i == 0 ? -1 : row[i - 1];
+    int cur = i == nnz ? nRow : row[i];
+    for (int r = prev + 1; r <= cur; r++) ptr[r] = i;
+}
+
+int build_row_ptr(const int *row_d, int nnz, int nRow, int *ptr_d, cudaStream_t s)
+{
+    row_ptr_kernel<<<ceil_div((long long)nnz + 1, 256), 256, 0, s>>>(row_d, nnz, nRow, ptr_d);
+    B2_KERNEL_CHECK();
+    return B200SPMV_OK;
+}
+
+__global__ void max_len_kernel(const int *__restrict__ ptr, int nRow, int *out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = r < nRow ? ptr[r + 1] - ptr[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
+int max_row_length(const int *ptr_d, int nRow, int *out_h, cudaStream_t s)
+{
+    DevBuf<int> m;
+    B2_TRY(m.alloc(1));
+    B2_CUDA(cudaMemsetAsync(m.p, 0, sizeof(int), s));
+    if (nRow > 0) {
+        max_len_kernel<<<ceil_div(nRow, 256), 256, 0, s>>>(ptr_d, nRow, m.p);
+        B2_KERNEL_CHECK();
+    }
+    B2_CUDA(cudaMemcpyAsync(out_h, m.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return B200SPMV_OK;
+}
+
+template <typename T> static int exclusive_scan_t(const T *in_d, T *out_d, int n, cudaStream_t s)
+{
+    if (n <= 0) return B200SPMV_OK;
+    size_t tmp = 0;
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in_d, out_d, n, s));
+    DevBuf<char> t;
+    B2_TRY(t.alloc(tmp));
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(t.p, tmp, in_d, out_d, n, s));
+    B2_CUDA(cudaStreamSynchronize(s));   // temp storage dies with this frame
+    return B200SPMV_OK;
+}
+int exclusive_scan_i32(const int *in_d, int *out_d, int n, cudaStream_t s) { return exclusive_scan_t(in_d, out_d, n, s); }
+int exclusive_scan_i64(const long long *in_d, long long *out_d, int n, cudaStream_t s) { return exclusive_scan_t(in_d, out_d, n, s); }
+
+// ---------------------------------------------------------------- input contract
+__global__ void validate_kernel(const int *__restrict__ row, const int *__restrict__ col, int nnz,
+                                int nRow, int nCol, int *bad)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    int r = row[i], c = col[i];
+    bool wrong = r < 0 || r >= nRow || c < 0 || c >= nCol;
+    if (i > 0 && !wrong) {
+        int pr = row[i - 1], pc = col[i - 1];
+        wrong = pr > r || (pr == r && pc >= c);
+    }
+    if (wrong) atomicMin(bad, i);
+}
+
+int validate_sorted_coo(const CooView &A, cudaStream_t s)
+{
+    if (A.nnz == 0) return B200SPMV_OK;
+    DevBuf<int> bad;
+    B2_TRY(bad.alloc(1));
+    int init = 0x7fffffff, got = 0;
+    B2_CUDA(cudaMemcpyAsync(bad.p, &init, sizeof(int), cudaMemcpyHostToDevice, s));
+    validate_kernel<<<ceil_div(A.nnz, 256), 256, 0, s>>>(A.row, A.col, A.nnz, A.nRow, A.nCol, bad.p);
+    B2_KERNEL_CHECK();
+    B2_CUDA(cudaMemcpyAsync(&got, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if (got != init) {
+        set_error("convert: COO entry %d breaks the input contract (sorted by (row,col), no "
+                  "duplicates, 0 <= row < nRow, 0 <= col < nCol; reference src/util.cpp:51)", got);
+        return B200SPMV_ERR_INVALID;
+    }
+    return B200SPMV_OK;
+}
+
+}  // namespace b2

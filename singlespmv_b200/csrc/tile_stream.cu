@@ -1,0 +1,193 @@
+// tile_stream.cu -- kernels of the tile-stream multiply (see tile_stream.cuh).
+#include "tile_stream.cuh"
+
+namespace b2 {
+
+// tile_row[t] = first row r with row_ptr[r] >= t*TS_TILE (lower bound over row_ptr[0..nRow]).
+// Rows [tile_row[t], tile_row[t+1]) are OWNED by tile t: their first entry lies in it.  Empty
+// rows are owned by the tile that contains their (shared) position; trailing rows by the last.
+__global__ void tile_row_kernel(const int *__restrict__ ptr, int nRow, int nTiles, int *__restrict__ tile_row)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nTiles) return;
+    if (t == nTiles) {
+        tile_row[t] = nRow;
+        return;
+    }
+    int key = t * TS_TILE, lo = 0, hi = nRow + 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ptr[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_row[t] = lo;
+}
+
+__global__ void __launch_bounds__(TS_THREADS)
+tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
+                   const double *__restrict__ val, const int *__restrict__ tile_row,
+                   const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
+                   int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok)
+{
+    __shared__ __align__(16) double prod[TS_TILE];
+    __shared__ int long_row[TS_MAXLONG];
+    __shared__ int n_long;
+
+    const int tid = threadIdx.x;
+    const int t = tileLo + blockIdx.x;
+    const int t0 = t * TS_TILE;
+    const int t1 = min(t0 + TS_TILE, nnz);
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_x = policy_evict_last();
+    if (tid == 0) n_long = 0;
+
+    // ---- phase 1: stream the tile, gather x, park products in shared memory
+    if (t1 - t0 == TS_TILE && vec_ok) {
+        int4 c[TS_IPT / 4];
+        double2 v[TS_IPT / 2];
+#pragma unroll
+        for (int k = 0; k < TS_IPT / 4; k++) {
+            const int e = t0 + 4 * (tid + k * TS_THREADS);
+            c[k] = ld_stream_i4(col + e, pol_stream);
+            v[2 * k] = ld_stream_d2(val + e, pol_stream);
+            v[2 * k + 1] = ld_stream_d2(val + e + 2, pol_stream);
+        }
+        double xs[TS_IPT];
+#pragma unroll
+        for (int k = 0; k < TS_IPT / 4; k++) {
+            xs[4 * k + 0] = ld_x(x + c[k].x, pol_x);
+            xs[4 * k + 1] = ld_x(x + c[k].y, pol_x);
+            xs[4 * k + 2] = ld_x(x + c[k].z, pol_x);
+            xs[4 * k + 3] = ld_x(x + c[k].w, pol_x);
+        }
+#pragma unroll
+        for (int k = 0; k < TS_IPT / 4; k++) {
+            double2 *dst = reinterpret_cast<double2 *>(prod + 4 * (tid + k * TS_THREADS));
+            dst[0] = make_double2(__dmul_rn(v[2 * k].x, xs[4 * k]), __dmul_rn(v[2 * k].y, xs[4 * k + 1]));
+            dst[1] = make_double2(__dmul_rn(v[2 * k + 1].x, xs[4 * k + 2]),
+                                  __dmul_rn(v[2 * k + 1].y, xs[4 * k + 3]));
+        }
+    } else {
+        for (int i = tid; i < t1 - t0; i += TS_THREADS)
+            prod[i] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream),
+                                ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
+    }
+
+    const int r_lo = tile_row[t], r_hi = tile_row[t + 1];
+    const int first = row_ptr[r_lo];          // r_lo <= nRow, row_ptr[nRow] = nnz
+    const int cin_end = min(first, t1);       // [t0, cin_end) belongs to row r_lo-1
+    __syncthreads();
+
+    // ---- phase 2a: one thread per owned row, in-tile row-bin scheduler
+    for (int r = r_lo + tid; r < r_hi; r += TS_THREADS) {
+        if (r < rowLo || r >= rowHi) continue;
+        const int b = row_ptr[r], e_full = row_ptr[r + 1];
+        const int e = min(e_full, t1);
+        if (e_full > t1 && e_full - b <= TS_LONG) continue;   // short row crossing: fix-up recomputes it
+        if (e - b > TS_LONG) {
+            long_row[atomicAdd(&n_long, 1)] = r;
+            continue;
+        }
+        double acc = 0.0;
+        for (int j = b; j < e; j++) acc = __dadd_rn(acc, prod[j - t0]);
+        y[r] = accumulate ? __dadd_rn(y[r], acc) : acc;
+    }
+    if (tid == 0 && cin_end > t0) {
+        const int rc = r_lo - 1;
+        if (first - row_ptr[rc] > TS_LONG && rc >= rowLo && rc < rowHi)
+            long_row[atomicAdd(&n_long, 1)] = -1;
+    }
+    __syncthreads();
+
+    // ---- phase 2b: one warp per long row / carried-in piece
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nl = n_long;
+    for (int i = warp; i < nl; i += TS_THREADS / 32) {
+        const int r = long_row[i];
+        int b, e;
+        if (r < 0) {
+            b = t0;
+            e = cin_end;
+        } else {
+            b = row_ptr[r];
+            e = min(row_ptr[r + 1], t1);
+        }
+        double acc = 0.0;
+        for (int j = b + lane; j < e; j += 32) acc += prod[j - t0];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (r < 0) carry[t] = acc;
+            else y[r] = accumulate ? y[r] + acc : acc;
+        }
+    }
+}
+
+// Finishes the rows that cross tile boundaries; one thread per tile, only the FIRST carrying
+// tile of a row acts.  Short rows are recomputed from global memory in the reference's order.
+__global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
+                                  const double *__restrict__ val, const int *__restrict__ tile_row,
+                                  const double *__restrict__ x, double *__restrict__ y,
+                                  const double *__restrict__ carry, int tileLo, int tileHi, int rowLo,
+                                  int rowHi, int accumulate)
+{
+    const int t = tileLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tileHi || t == 0) return;
+    const int t0 = t * TS_TILE;
+    const int r0 = tile_row[t];
+    const int e = row_ptr[r0];
+    if (e <= t0) return;                       // a row starts exactly at the tile start
+    const int rc = r0 - 1;
+    if (rc < rowLo || rc >= rowHi) return;
+    const int b = row_ptr[rc];
+    if (t != b / TS_TILE + 1) return;
+    if (e - b <= TS_LONG) {
+        double acc = 0.0;
+        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn(val[j], x[col[j]]));
+        y[rc] = accumulate ? __dadd_rn(y[rc], acc) : acc;
+    } else {
+        const int last = (e - 1) / TS_TILE;
+        double sum = 0.0;
+        for (int u = t; u <= last; u++) sum += carry[u];
+        y[rc] += sum;
+    }
+}
+
+int TileStream::build(const int *row_ptr_d, const int *col_d, const double *val_d, int nRow_, int nnz_,
+                      cudaStream_t s)
+{
+    row_ptr = row_ptr_d;
+    col = col_d;
+    val = val_d;
+    nRow = nRow_;
+    nnz = nnz_;
+    nTiles = ceil_div(nnz, TS_TILE);
+    B2_TRY(tile_row.alloc((size_t)nTiles + 1));
+    B2_TRY(carry.alloc((size_t)nTiles));
+    tile_row_kernel<<<ceil_div(nTiles + 1, 256), 256, 0, s>>>(row_ptr, nRow, nTiles, tile_row.p);
+    B2_KERNEL_CHECK();
+    return B200SPMV_OK;
+}
+
+int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo,
+                    int tileHi, cudaStream_t s) const
+{
+    if (rowHi <= rowLo) return B200SPMV_OK;
+    if (nTiles == 0) {   // no non-zeros at all: y = 0 (beta = 0)
+        if (!accumulate) B2_CUDA(cudaMemsetAsync(y + rowLo, 0, sizeof(double) * (size_t)(rowHi - rowLo), s));
+        return B200SPMV_OK;
+    }
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
+    tile_stream_kernel<<<tileHi - tileLo, TS_THREADS, 0, s>>>(row_ptr, col, val, tile_row.p, x, y, carry.p,
+                                                             nnz, tileLo, rowLo, rowHi, accumulate ? 1 : 0,
+                                                             vec_ok);
+    B2_KERNEL_CHECK();
+    if (tileHi - tileLo > 1 || tileLo > 0) {
+        tile_fixup_kernel<<<ceil_div(tileHi - tileLo, 256), 256, 0, s>>>(row_ptr, col, val, tile_row.p, x, y,
+                                                                        carry.p, tileLo, tileHi, rowLo, rowHi,
+                                                                        accumulate ? 1 : 0);
+        B2_KERNEL_CHECK();
+    }
+    return B200SPMV_OK;
+}
+
+}  // namespace b2

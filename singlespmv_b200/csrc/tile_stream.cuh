@@ -1,0 +1,51 @@
+// tile_stream.cuh -- the nnz-balanced "tile stream" multiply shared by CRS, SS and CSS.
+//
+// The non-zero stream is cut into fixed tiles of TS_TILE entries, one CTA per tile, so every
+// CTA moves the same number of bytes whatever the row-length distribution (R-MAT rows span
+// 0 ... 10^5+).  A CTA
+//   1. streams its col/val slice with 128-bit loads (L1 no-allocate, L2 evict-first), gathers x
+//      and parks the products in shared memory -- never in HBM (the reference's SS plugin
+//      materialises them in val_buf, src/opt_ss.cpp:226-238, costing +16 B/nnz);
+//   2. reduces the rows it OWNS (rows whose first entry lies in the tile) with an in-tile row-bin
+//      scheduler: short rows one thread each, sequentially in ascending column order with
+//      unfused mul/add (bit-identical to reference src/opt_crs.cpp:61-67); long rows one warp
+//      each (lanes stride, shuffle tree); the piece of a row carried in from the previous tile
+//      is reduced by a warp into carry[tile].
+// A second, tiny kernel finishes rows that cross tile boundaries: short ones are recomputed
+// sequentially (so EVERY row up to TS_LONG entries is bit-exact), long ones get their carries
+// added in tile order (deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int TS_THREADS = 256;
+constexpr int TS_IPT = 8;
+constexpr int TS_TILE = TS_THREADS * TS_IPT;   // 2048 non-zeros = 24 KB of matrix per CTA
+constexpr int TS_LONG = 64;                    // rows longer than this are reduced by a warp
+constexpr int TS_MAXLONG = TS_TILE / TS_LONG + 2;
+
+struct TileStream {
+    // borrowed
+    const int *row_ptr = nullptr;   // [nRow+1]
+    const int *col = nullptr;       // [nnz] (may be padded beyond nnz; padding is never read)
+    const double *val = nullptr;
+    int nRow = 0, nnz = 0;
+    // owned
+    int nTiles = 0;
+    DevBuf<int> tile_row;           // [nTiles+1]: first row whose first entry is >= tile start
+    DevBuf<double> carry;           // [nTiles]
+
+    int build(const int *row_ptr_d, const int *col_d, const double *val_d, int nRow_, int nnz_,
+              cudaStream_t s);
+    // y[rowLo..rowHi) = (accumulate ? y : 0) + A x, restricted to tiles [tileLo, tileHi)
+    int run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo, int tileHi,
+            cudaStream_t s) const;
+    int run_all(const double *x, double *y, bool accumulate, cudaStream_t s) const
+    {
+        return run(x, y, accumulate, 0, nRow, 0, nTiles, s);
+    }
+    size_t meta_bytes() const { return tile_row.bytes(); }
+};
+
+}  // namespace b2

@@ -54,6 +54,7 @@ class Oracle:
         L.synth_stencil_nnz.restype = C.c_longlong
         L.synth_stencil.restype = C.c_longlong
         L.synth_rmat.restype = C.c_longlong
+        L.synth_stencil_range.restype = C.c_longlong
 
     # ---- CRS (reference src/opt_crs.cpp)
     def crs_convert(self, nRow, row, col, val):
@@ -255,6 +256,17 @@ class Oracle:
         got = self.lib.synth_stencil(C.c_int(k), C.c_int(n), row.ctypes, col.ctypes, val.ctypes)
         assert got == nnz
         return int(nRow), int(nRow), row, col, val
+
+    def stencil_rows(self, kind, n, row_begin, row_end):
+        k = {"lap2d5": 0, "lap3d7": 1, "box3d27": 2}[kind]
+        nRow = int(self.lib.synth_stencil_rows(C.c_int(k), C.c_int(n)))
+        cap = (row_end - row_begin) * (5, 7, 27)[k]
+        row = np.empty(cap, np.int32)
+        col = np.empty(cap, np.int32)
+        val = np.empty(cap, np.float64)
+        got = self.lib.synth_stencil_range(C.c_int(k), C.c_int(n), C.c_int(row_begin), C.c_int(row_end),
+                                           row.ctypes, col.ctypes, val.ctypes)
+        return nRow, nRow, row[:got].copy(), col[:got].copy(), val[:got].copy()
 
     def uniform(self, seed, nRow, nCol, K, row_begin=0, row_end=None):
         row_end = nRow if row_end is None else row_end
