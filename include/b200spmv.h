@@ -141,6 +141,37 @@ B200SPMV_API int b200spmv_coo_free(b200spmv_coo *coo);
 /* Copies the triplets to host arrays of coo->nnz entries (parity checks, CPU baseline input). */
 B200SPMV_API int b200spmv_coo_download(const b200spmv_coo *coo, int *row_h, int *col_h, double *val_h);
 
+/* ---- row-partitioned multi-GPU multiply.  The reference is single-node OpenMP
+ * (its only "distribution" is the static row schedule of src/opt_crs.cpp:57-58); this is the
+ * B200 design for BASELINE.json config 5: contiguous row blocks balanced by non-zero count, x
+ * distributed like the rows, per multiply only the referenced remote x entries ("halo") move.
+ * One process per GPU; the host side (singlespmv_b200/dist.py) carries the exchange over
+ * NCCL/NVLink and overlaps it with the interior rows via b200spmv_multiply_rows. */
+/* bounds_h[0..nParts]: block g owns rows [bounds[g], bounds[g+1]), split where the running
+ * non-zero count passes g*nnz/nParts. */
+B200SPMV_API int b200spmv_partition_rows(const int *row_d /* sorted COO row ids */, long long nnz, int nRow,
+                            int nParts, int *bounds_h);
+/* the same split for a synthetic matrix, from its row lengths alone (nothing is generated) */
+B200SPMV_API int b200spmv_partition_synth(int kind, long long p0, long long p1, int nParts, int *bounds_h);
+
+typedef struct b200spmv_halo b200spmv_halo;
+/* coo holds rows [rowBegin,rowEnd) with GLOBAL ids; the block owns x[colBegin,colEnd).  In place:
+ * rows become block-local and columns get the monotone local numbering
+ *   [left halo | owned slice | right halo]   (halo = referenced remote columns, ascending),
+ * so rows stay sorted and are summed in the single-GPU order.  coo->nRow/nCol become the local
+ * dimensions; convert it with any format afterwards. */
+B200SPMV_API int b200spmv_halo_plan(b200spmv_coo *coo, int colBegin, int colEnd, b200spmv_halo **out, void *stream);
+/* info8 = nLocal, nLeft, nRight, interiorBegin, interiorEnd, nSend, rowBegin, rowEnd.  Local rows
+ * [interiorBegin, interiorEnd) reference owned columns only. */
+B200SPMV_API int b200spmv_halo_info(const b200spmv_halo *h, long long *info8);
+/* the halo's global column ids (get_array size protocol) -- what this block asks its peers for */
+B200SPMV_API long long b200spmv_halo_cols(const b200spmv_halo *h, int *cols_h, long long cap_bytes);
+/* global ids of OWNED columns the peers asked for, concatenated in peer order */
+B200SPMV_API int b200spmv_halo_set_send(b200spmv_halo *h, const int *send_cols_h, long long n);
+/* sendbuf[i] = x_owned[send column i]: one gather kernel per multiply */
+B200SPMV_API int b200spmv_halo_pack(const b200spmv_halo *h, const double *x_owned_d, double *sendbuf_d, void *stream);
+B200SPMV_API int b200spmv_halo_free(b200spmv_halo *h);
+
 /* x = rand()/RAND_MAX stream of src/util.cpp:92-102 after srand(seed) (src/main.cpp:18):
  * writes x_h[0..nCol) (and y_h[0..nRow) if y_h != NULL), host side, glibc rand(). */
 B200SPMV_API int b200spmv_reference_vectors(unsigned seed, int nCol, int nRow, double *x_h, double *y_h);

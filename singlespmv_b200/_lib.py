@@ -55,6 +55,15 @@ def _load():
     lib.b200spmv_coo_free.argtypes = [C.POINTER(Coo)]
     lib.b200spmv_coo_download.argtypes = [C.POINTER(Coo), vp, vp, vp]
     lib.b200spmv_reference_vectors.argtypes = [C.c_uint, ip, ip, vp, vp]
+    lib.b200spmv_partition_rows.argtypes = [vp, ll, ip, ip, vp]
+    lib.b200spmv_partition_synth.argtypes = [ip, ll, ll, ip, vp]
+    lib.b200spmv_halo_plan.argtypes = [C.POINTER(Coo), ip, ip, C.POINTER(vp), vp]
+    lib.b200spmv_halo_info.argtypes = [vp, vp]
+    lib.b200spmv_halo_cols.argtypes = [vp, vp, ll]
+    lib.b200spmv_halo_cols.restype = ll
+    lib.b200spmv_halo_set_send.argtypes = [vp, vp, ll]
+    lib.b200spmv_halo_pack.argtypes = [vp, vp, vp, vp]
+    lib.b200spmv_halo_free.argtypes = [vp]
     return lib
 
 

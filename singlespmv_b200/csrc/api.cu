@@ -47,6 +47,16 @@ static int require_device()
                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
         return B200SPMV_ERR_CUDA;
     }
+    // L2 fetch granularity: a missing 32-byte sector normally pulls 64 bytes from HBM, which doubles
+    // the DRAM traffic of random x gathers.  B200SPMV_L2_FETCH=32|64|128 sets the device limit once.
+    static bool limit_done = false;
+    if (!limit_done) {
+        limit_done = true;
+        const char *g = getenv("B200SPMV_L2_FETCH");
+        if (g && atoi(g) > 0) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)) != cudaSuccess) cudaGetLastError();
+        }
+    }
     return B200SPMV_OK;
 }
 

@@ -4,12 +4,6 @@ namespace b2 {
 #ifndef HAVE_COO
 Format *make_coo(const b200spmv_options &) { return nullptr; }
 #endif
-#ifndef HAVE_JDS
-Format *make_jds(const b200spmv_options &) { return nullptr; }
-#endif
-#ifndef HAVE_DIA
-Format *make_dia(const b200spmv_options &) { return nullptr; }
-#endif
 #ifndef HAVE_SS
 Format *make_ss(const b200spmv_options &) { return nullptr; }
 #endif

@@ -1,0 +1,320 @@
+"""Row-partitioned multi-GPU SpMV: one process per GPU, x halo over NCCL/NVLink.
+
+The reference has no distributed code (single-node OpenMP; src/opt_crs.cpp:57-58 is its only "partition":
+a static row schedule).  BASELINE.json config 5 asks for the CRS multiply row-partitioned by non-zero
+balance with the x halo exchange overlapped with the local block.  Layering:
+
+* device work (partition by nnz, halo discovery, column renumbering, pack kernel, multiply of a row range)
+  is behind the C-ABI: b200spmv_partition_*, b200spmv_halo_*, b200spmv_multiply_rows;
+* this file is host plumbing only: who asks whom for which x entries (``plan_requests``), and per multiply
+  the grouped NCCL send/recv on a communication stream while the interior rows run on the compute stream.
+
+Per multiply on every rank:
+    comm stream   : pack owned x entries the peers need -> grouped isend/irecv straight into x_ext's halo slots
+    compute stream: rows that touch no halo column            (b200spmv_multiply_rows, > 99 % of config 5)
+    compute stream: after the receives land, the boundary rows at both ends of the block
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import SYNTH, Coo, check, lib
+from .plugin import DeviceCoo, SpMatOpt, _ptr
+
+
+# ------------------------------------------------------------------------------------------ host logic (no GPU needed)
+def owner_counts(halo_cols, bounds):
+    """How many of the (ascending, global) halo columns each block owns.  bounds: nParts+1 row/col splits."""
+    halo_cols = np.asarray(halo_cols)
+    edges = np.searchsorted(halo_cols, np.asarray(bounds), side="left")
+    return np.diff(edges).astype(np.int64)
+
+
+def plan_requests(halo_cols, bounds, rank, all_to_all_counts, all_to_all_lists):
+    """Tell every owner which of its x entries this rank needs; learn what the peers need from us.
+
+    all_to_all_counts(send_counts[nParts]) -> recv_counts[nParts]
+    all_to_all_lists(send_list, send_counts, recv_counts) -> recv_list     (int32 global column ids)
+    Returns (recv_counts = x entries arriving from each peer, send_counts = entries leaving to each peer,
+             send_cols = global ids of owned columns to pack, in peer order)."""
+    need = owner_counts(halo_cols, bounds)
+    if need[rank] != 0:
+        raise ValueError("halo of rank %d contains %d owned columns" % (rank, need[rank]))
+    asked = np.asarray(all_to_all_counts(need), dtype=np.int64)
+    send_cols = np.asarray(all_to_all_lists(np.ascontiguousarray(halo_cols, np.int32), need, asked), dtype=np.int32)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    if len(send_cols) and (send_cols.min() < lo or send_cols.max() >= hi):
+        raise ValueError("rank %d was asked for columns it does not own" % rank)
+    return need, asked, send_cols
+
+
+class Block:
+    """One rank's share: local matrix (any format, default CRS), halo bookkeeping, device buffers."""
+
+    def __init__(self, kind, p0, p1, seed, bounds, rank, fmt="crs", stream=None):
+        import torch
+        self.rank, self.bounds = rank, [int(b) for b in bounds]
+        rb, re = self.bounds[rank], self.bounds[rank + 1]
+        coo = DeviceCoo(kind, p0, p1, seed, rb, re) if re > rb else None
+        if coo is None:
+            raise ValueError("rank %d owns no rows" % rank)
+        self.global_nnz_local = coo.nNnz
+        self.halo = C.c_void_p()
+        check(lib.b200spmv_halo_plan(C.byref(coo.c), rb, re, C.byref(self.halo), stream))
+        info = (C.c_longlong * 8)()
+        check(lib.b200spmv_halo_info(self.halo, info))
+        self.nLocal, self.nLeft, self.nRight, self.interiorBegin, self.interiorEnd = (int(v) for v in info[:5])
+        self.nRows = re - rb
+        self.A = SpMatOpt(fmt).convert_device(coo, nRow=self.nRows, stream=stream)
+        coo.free()
+        n = lib.b200spmv_halo_cols(self.halo, None, 0)
+        check(n)
+        self.halo_cols = np.empty(n // 4, np.int32)
+        if n:
+            check(lib.b200spmv_halo_cols(self.halo, _ptr(self.halo_cols), n))
+        self.x_ext = torch.zeros(self.nLeft + self.nLocal + self.nRight, dtype=torch.float64, device="cuda")
+        self.y = torch.full((self.nRows,), float("nan"), dtype=torch.float64, device="cuda")
+        self.sendbuf = None
+        self.recv_counts = self.send_counts = None
+
+    @property
+    def x_owned(self):
+        return self.x_ext[self.nLeft:self.nLeft + self.nLocal]
+
+    def set_requests(self, recv_counts, send_counts, send_cols):
+        import torch
+        self.recv_counts, self.send_counts = [int(v) for v in recv_counts], [int(v) for v in send_counts]
+        send_cols = np.ascontiguousarray(send_cols, np.int32)
+        check(lib.b200spmv_halo_set_send(self.halo, _ptr(send_cols), len(send_cols)))
+        self.sendbuf = torch.empty(max(1, len(send_cols)), dtype=torch.float64, device="cuda")
+        # views: where each peer's entries land in x_ext / leave from sendbuf
+        self.recv_views, self.send_views = {}, {}
+        off = 0
+        for p, c in enumerate(self.recv_counts):
+            if c:
+                base = off if p < self.rank else self.nLocal + off     # left halo first, right halo after the owned slice
+                self.recv_views[p] = self.x_ext[base:base + c]
+            off += c
+        off = 0
+        for p, c in enumerate(self.send_counts):
+            if c:
+                self.send_views[p] = self.sendbuf[off:off + c]
+            off += c
+
+    def pack(self, stream_ptr=None):
+        check(lib.b200spmv_halo_pack(self.halo, C.c_void_p(self.x_owned.data_ptr()), C.c_void_p(self.sendbuf.data_ptr()), stream_ptr))
+
+    def multiply_interior(self, stream_ptr=None):
+        if self.interiorEnd > self.interiorBegin:
+            self.A.multiply_rows(self.interiorBegin, self.interiorEnd, self.x_ext.data_ptr(), self.y.data_ptr(), stream_ptr)
+
+    def multiply_boundary(self, stream_ptr=None):
+        if self.interiorBegin > 0:
+            self.A.multiply_rows(0, self.interiorBegin, self.x_ext.data_ptr(), self.y.data_ptr(), stream_ptr)
+        if self.interiorEnd < self.nRows:
+            self.A.multiply_rows(self.interiorEnd, self.nRows, self.x_ext.data_ptr(), self.y.data_ptr(), stream_ptr)
+
+    def launches_per_step(self):
+        per = self.A.scalar("launches")
+        parts = (self.interiorEnd > self.interiorBegin) + (self.interiorBegin > 0) + (self.interiorEnd < self.nRows)
+        return per * parts + (1 if self.sendbuf is not None and sum(self.send_counts) else 0)
+
+    def free(self):
+        if self.halo:
+            lib.b200spmv_halo_free(self.halo)
+            self.halo = C.c_void_p()
+        self.A.destroy()
+
+
+def synth_bounds(kind, p0, p1, nParts):
+    b = np.empty(nParts + 1, np.int32)
+    check(lib.b200spmv_partition_synth(SYNTH[kind], int(p0), int(p1), nParts, _ptr(b)))
+    return b
+
+
+# ------------------------------------------------------------------------------------------ all ranks in one process (tests)
+def build_local_group(kind, p0, p1, seed, nParts, fmt="crs"):
+    """All blocks on ONE GPU in one process: the same device code and the same request planning as the
+    NCCL path, with device-to-device copies standing in for send/recv (parity tests on a 1-GPU box)."""
+    bounds = synth_bounds(kind, p0, p1, nParts)
+    blocks = [Block(kind, p0, p1, seed, bounds, r, fmt) for r in range(nParts)]
+    need = [owner_counts(b.halo_cols, bounds) for b in blocks]
+    for r, b in enumerate(blocks):
+        asked = np.array([need[p][r] for p in range(nParts)], np.int64)
+        lists = []
+        for p in range(nParts):
+            off = int(need[p][:r].sum())
+            lists.append(blocks[p].halo_cols[off:off + int(need[p][r])])
+        send_cols = np.concatenate(lists) if lists else np.empty(0, np.int32)
+        b.set_requests(need[r], asked, send_cols)
+    return bounds, blocks
+
+
+def local_group_multiply(blocks):
+    for b in blocks:
+        b.pack()
+        b.multiply_interior()
+    for b in blocks:
+        for p, view in b.recv_views.items():
+            view.copy_(blocks[p].send_views[b.rank])
+    for b in blocks:
+        b.multiply_boundary()
+
+
+# ------------------------------------------------------------------------------------------ torch.distributed path
+def _dist_plan(block, world, device):
+    import torch
+    import torch.distributed as dist
+
+    def a2a_counts(send):
+        s = torch.tensor(send, dtype=torch.int64, device=device)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s)
+        return r.cpu().numpy()
+
+    def a2a_lists(send_list, send_counts, recv_counts):
+        s = torch.from_numpy(send_list).to(device)
+        r = torch.empty(int(sum(recv_counts)), dtype=torch.int32, device=device)
+        dist.all_to_all_single(r, s, [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        return r.cpu().numpy()
+
+    return plan_requests(block.halo_cols, block.bounds, block.rank, a2a_counts, a2a_lists)
+
+
+class DistSpmv:
+    """The per-rank engine used by bench.py --gpus N (and usable as a library)."""
+
+    def __init__(self, kind, p0, p1, seed, fmt="crs"):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.bounds = synth_bounds(kind, p0, p1, self.world)
+        self.block = Block(kind, p0, p1, seed, self.bounds, self.rank, fmt)
+        need, asked, send_cols = _dist_plan(self.block, self.world, self.device)
+        self.block.set_requests(need, asked, send_cols)
+        self.compute = torch.cuda.current_stream()
+        self.comm = torch.cuda.Stream()
+        self.done = torch.cuda.Event()
+        self.done.record(self.compute)
+
+    def exchange_async(self):
+        """Grouped NCCL send/recv of the halo on the comm stream.  Returns the work handles."""
+        import torch
+        import torch.distributed as dist
+        b = self.block
+        self.comm.wait_event(self.done)                      # previous step's readers of x_ext are finished
+        with torch.cuda.stream(self.comm):
+            b.pack(C.c_void_p(self.comm.cuda_stream))
+            ops = [dist.P2POp(dist.irecv, v, p) for p, v in b.recv_views.items()]
+            ops += [dist.P2POp(dist.isend, v, p) for p, v in b.send_views.items()]
+            return dist.batch_isend_irecv(ops) if ops else []
+
+    def step(self):
+        b = self.block
+        cptr = C.c_void_p(self.compute.cuda_stream)
+        works = self.exchange_async()
+        b.multiply_interior(cptr)                            # overlaps the exchange
+        for w in works:
+            w.wait()                                         # compute stream waits for the receives
+        b.multiply_boundary(cptr)
+        self.done.record(self.compute)
+
+
+def run_partitioned_bench(args, wl, wl_key):
+    """bench.py --gpus N (N > 1): strong scaling of one matrix over N ranks, launched by torchrun."""
+    import json
+    import os
+    import time
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler, peaks
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    fmt = args.format or "crs"
+    eng = DistSpmv(wl["kind"], wl["p0"], wl["p1"], wl["seed"], fmt)
+    b = eng.block
+    nRow = int(eng.bounds[-1])
+    # x: every rank fills its owned slice from the reference's rand() stream (src/main.cpp:18,31)
+    from .plugin import reference_vectors
+    x_h, _ = reference_vectors(nRow, 0, 3)
+    lo, hi = int(eng.bounds[rank]), int(eng.bounds[rank + 1])
+    x_pin = torch.from_numpy(x_h[lo:hi].copy()).pin_memory()
+    y_pin = torch.empty(b.nRows, dtype=torch.float64).pin_memory()
+    del x_h
+    b.x_owned.copy_(x_pin, non_blocking=True)
+    torch.cuda.synchronize()
+
+    nnz_t = torch.tensor([b.global_nnz_local, b.A.scalar("alg_bytes"), b.nLeft + b.nRight], dtype=torch.int64, device="cuda")
+    dist.all_reduce(nnz_t)
+    nnz, alg_bytes_sum, halo_total = (int(v) for v in nnz_t.tolist())
+    # compulsory bytes of the GLOBAL multiply (SURVEY.md 8d CRS formula), not the sum of the local ones
+    alg_bytes = 12 * nnz + 4 * (nRow + 1) + 8 * nRow + 8 * nRow
+
+    for _ in range(args.warmup):
+        eng.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a.record(eng.compute)
+    for _ in range(args.steps):
+        eng.step()
+    e.record(eng.compute)
+    torch.cuda.synchronize()
+    ms_local = a.elapsed_time(e)
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    dist.barrier()
+
+    # e2e: per step H2D of the owned x slice, exchange + multiply, D2H of the owned y slice
+    def e2e_step():
+        b.x_owned.copy_(x_pin, non_blocking=True)
+        eng.step()
+        y_pin.copy_(b.y, non_blocking=True)
+        eng.done.record(eng.compute)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_local = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    launches = torch.tensor([b.launches_per_step()], dtype=torch.int64, device="cuda")
+    dist.all_reduce(launches)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        line = {"metric": "SpMV GFLOP/s", "value": 2.0 * nnz / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "nRow": nRow, "nCol": nRow, "nnz": nnz,
+                           "parallelism": "row blocks by nnz balance x%d, x halo %d doubles/step over NCCL send/recv "
+                                          "overlapped with interior rows" % (world, halo_total),
+                           "l2": "inputs larger than L2 (%.2f GB per GPU per step)" % (alg_bytes / world / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / (peak * world), "traffic": None,
+                             "peak_source": peak_src + " x %d GPUs" % world, "alg_bytes_per_launch": alg_bytes,
+                             "kernel": "tile_stream_kernel (CRS), whole step incl. exposed halo exchange"},
+                "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
+                        "h2d_bytes_per_step": 8 * nRow, "d2h_bytes_per_step": 8 * nRow},
+                "gpu_launches": int(launches.item()) * args.steps, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

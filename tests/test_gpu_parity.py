@@ -146,6 +146,102 @@ def test_ell_golden(sp, name):
     assert np.array_equal(y, g["ell.y"])
 
 
+# ------------------------------------------------------------------------------------------ JDS
+def test_jds(sp, oracle, all_cases):
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        m = oracle.jds_convert(nRow, row, col, val)               # stable convention: ties by ascending row
+        A_opt, y = run_host(sp, "jds", nRow, nCol, row, col, val, x)
+        assert A_opt.scalar("maxLength") == m["maxLength"], name
+        for k in ("perm", "length", "ptr", "col_idx"):
+            assert np.array_equal(A_opt.array(k, np.int32), m[k]), (name, k)
+        assert np.array_equal(A_opt.array("val", np.float64), m["val"]), name
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        short = np.diff(oracle.crs_convert(nRow, row, col, val)["ptr"]) <= 2048
+        assert np.array_equal(y[short], y_ref[short]), name       # thread-per-row: the reference's own order
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_jds_golden_reference_tie_order(sp, name):
+    """With the reference's own perm imposed (its std::sort is unstable), every array is bit-exact."""
+    g = load_golden(name)
+    nRow, nCol = int(g["nRow"]), int(g["nCol"])
+    A_opt = sp.SpMatOpt("jds")
+    A_opt.set_jds_perm(g["jds.perm"])
+    A_opt.convert_host(sp.SpMat(nRow, nCol, g["in_row"], g["in_col"], g["in_val"]))
+    assert A_opt.scalar("maxLength") == int(g["jds.maxLength"])
+    for k in ("perm", "length", "ptr", "col_idx"):
+        assert np.array_equal(A_opt.array(k, np.int32), g["jds." + k]), k
+    assert np.array_equal(A_opt.array("val", np.float64), g["jds.val"])
+    y = np.full(nRow, np.nan)
+    A_opt.multiply_host(g["x"], y)
+    assert np.array_equal(y, g["jds.y"])
+    # default (stable) order: same length/ptr, perm equal up to ties
+    B_opt, yb = run_host(sp, "jds", nRow, nCol, g["in_row"], g["in_col"], g["in_val"], g["x"])
+    assert np.array_equal(B_opt.array("ptr", np.int32), g["jds.ptr"])
+    pb = B_opt.array("perm", np.int32)
+    assert np.array_equal(g["jds.length"][pb], g["jds.length"][g["jds.perm"]])
+    assert np.array_equal(yb, g["jds.y"])
+
+
+def test_jds_rejects_bad_perm(sp):
+    A = sp.SpMat(3, 3, [0, 0, 1], [0, 1, 1], [1.0, 2.0, 3.0])
+    for perm in ([1, 0, 2], [0, 0, 1], [0, 1, 5]):
+        m = sp.SpMatOpt("jds")
+        m.set_jds_perm(perm)
+        with pytest.raises(sp.B200SpmvError):
+            m.convert_host(A)
+
+
+# ------------------------------------------------------------------------------------------ DIA
+def banded_cases(oracle):
+    rng = np.random.default_rng(11)
+    out = []
+    for kind, n in (("lap2d5", 33), ("lap3d7", 9), ("box3d27", 10), ("box3d27", 17)):
+        nr, nc, r, c, v = oracle.stencil(kind, n)
+        out.append(("%s_%d" % (kind, n), nr, nc, r, c, v, oracle.reference_vectors(nc, nr)[0]))
+    # rectangular band with random values, odd sizes (exercises unaligned window edges), 70 diagonals (direct kernel)
+    for nr, nc, offs in ((1031, 1100, [-40, -3, -2, 0, 1, 2, 7, 60, 61]), (777, 600, list(range(-35, 35)))):
+        rows, cols = [], []
+        for i in range(nr):
+            cs = [i + o for o in offs if 0 <= i + o < nc and rng.random() < 0.8]
+            rows += [i] * len(cs)
+            cols += cs
+        r, c = np.array(rows, np.int32), np.array(cols, np.int32)
+        out.append(("band_%dx%d" % (nr, nc), nr, nc, r, c, rng.standard_normal(len(r)), rng.random(nc)))
+    return out
+
+
+def test_dia(sp, oracle, all_cases):
+    small = [c for c in all_cases if c[1] * (c[1] + c[2]) < 3e7 and not c[0].startswith(("rmat", "onelong"))]
+    for name, nRow, nCol, row, col, val, x in small + banded_cases(oracle):
+        m = oracle.dia_convert(nRow, nCol, row, col, val)
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        A_opt, y = run_host(sp, "dia", nRow, nCol, row, col, val, x)
+        assert A_opt.scalar("nDiag") == m["nDiag"], name
+        assert np.array_equal(A_opt.array("ioff", np.int32), m["ioff"]), name
+        assert np.array_equal(A_opt.array("diag", np.float64), m["diag"].ravel()), name
+        assert np.array_equal(y, oracle.dia_spmv(m, x)), name     # ascending diagonals per row, unfused
+        assert np.array_equal(y, y_ref), name                     # ... which is also the CRS order
+    assert A_opt.scalar("tma") == 0                               # 70 diagonals -> direct kernel was covered
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_dia_golden(sp, name):
+    g = load_golden(name)
+    A_opt, y = run_host(sp, "dia", int(g["nRow"]), int(g["nCol"]), g["in_row"], g["in_col"], g["in_val"], g["x"])
+    assert A_opt.scalar("nDiag") == int(g["dia.nDiag"])
+    assert np.array_equal(A_opt.array("ioff", np.int32), g["dia.ioff"])
+    assert np.array_equal(A_opt.array("diag", np.float64), g["dia.diag"])
+    assert np.array_equal(y, g["dia.y"])
+
+
+def test_dia_tma_path_used(sp, oracle):
+    nr, nc, r, c, v = oracle.stencil("box3d27", 12)
+    A_opt, _ = run_host(sp, "dia", nr, nc, r, c, v, np.ones(nc))
+    assert A_opt.scalar("nDiag") == 27 and A_opt.scalar("nRuns") == 9 and A_opt.scalar("tma") == 1
+
+
 # ------------------------------------------------------------------------------------------ inputs
 def test_rejects_unsorted_and_duplicates(sp):
     x = np.ones(4)
@@ -206,3 +302,49 @@ def test_full_size_linearity_crs_ell(sp):
         assert torch.allclose(ys[2], lin, rtol=1e-12, atol=1e-12)
         out[name] = ys[0]
     assert torch.equal(out["crs"], out["ell"])          # both sum each row in ascending-column order
+
+
+# ------------------------------------------------------------------------------------------ row-partitioned path
+@pytest.mark.parametrize("kind,n,parts", [("lap3d7", 24, 2), ("lap3d7", 24, 5), ("box3d27", 14, 3), ("lap2d5", 90, 4)])
+def test_partitioned_blocks_match_single_gpu(sp, oracle, kind, n, parts):
+    """All blocks of the multi-GPU path on one device (device-to-device copies stand in for NCCL):
+    same device code (halo plan, renumbering, pack, multiply_rows) -> y bit-identical to the reference CRS."""
+    import torch
+    from singlespmv_b200 import dist as spd
+    nr, nc, row, col, val = oracle.stencil(kind, n)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    bounds, blocks = spd.build_local_group(kind, n, 0, 1, parts)
+    ptr = oracle.crs_convert(nr, row, col, val)["ptr"]
+    targets = [len(row) * g // parts for g in range(parts + 1)]
+    assert [int(b) for b in bounds] == [int(np.searchsorted(ptr, t, side="left")) for t in targets[:-1]] + [nr]
+    xd = torch.from_numpy(x).cuda()
+    for b in blocks:
+        lo, hi = int(bounds[b.rank]), int(bounds[b.rank + 1])
+        b.x_owned.copy_(xd[lo:hi])
+        assert b.interiorBegin <= b.interiorEnd
+    for _ in range(2):
+        spd.local_group_multiply(blocks)
+    torch.cuda.synchronize()
+    y = torch.cat([b.y for b in blocks]).cpu().numpy()
+    assert np.array_equal(y, y_ref)
+    # interior rows really are the bulk and really touch no halo
+    if kind == "lap3d7" and parts == 2:
+        assert blocks[0].nLeft == 0 and blocks[0].nRight == n * n and blocks[1].nLeft == n * n
+        assert blocks[0].interiorEnd - blocks[0].interiorBegin == blocks[0].nRows - n * n
+    for b in blocks:
+        b.free()
+
+
+def test_partition_rows_from_coo(sp, oracle):
+    import ctypes as C
+    from singlespmv_b200._lib import lib, check
+    d = sp.DeviceCoo("rmat", 12, 100000, 42)
+    _, _, row, col, val = d.to_host()
+    ptr = oracle.crs_convert(d.nRow, row, col, val)["ptr"]
+    for parts in (2, 8):
+        b = np.empty(parts + 1, np.int32)
+        check(lib.b200spmv_partition_rows(d.c.row_d, d.nNnz, d.nRow, parts, b.ctypes.data_as(C.c_void_p)))
+        assert b[0] == 0 and b[-1] == d.nRow and np.all(np.diff(b) >= 0)
+        per = np.diff(ptr[b])
+        assert per.max() - per.min() <= 2 * np.diff(ptr).max()        # balanced up to one row
