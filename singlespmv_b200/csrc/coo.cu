@@ -1,0 +1,188 @@
+// coo.cu -- COO plugin (/root/reference/src/opt_coo.{h,cpp}): the converted matrix IS the sorted
+// triplet list (the reference aliases the input arrays, opt_coo.cpp:14-19); multiply is y = 0 followed
+// by an `omp atomic` scatter-add per entry (:34-46).
+//
+// B200 multiply: no atomics, no zero-fill pass.  The entry stream is cut into tiles of COO_TILE
+// entries (one CTA each, equal bytes per CTA whatever the row lengths).  A CTA streams row/col/val
+// with 128-bit loads, parks the products and the row ids in shared memory and reduces every run of
+// equal row ids that STARTS in the tile: short runs one thread each, sequentially in storage order
+// with unfused mul/add (bit-identical to opt_crs.cpp:61-67), long runs one warp each (shuffle tree).
+// The thread that finds a run start also zero-fills the empty rows in front of it (beta = 0).  Runs
+// crossing a tile boundary are finished by a second tiny kernel (short: recomputed sequentially;
+// long: per-tile carries added in tile order -> deterministic).
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int COO_THREADS = 256;
+constexpr int COO_IPT = 8;
+constexpr int COO_TILE = COO_THREADS * COO_IPT;
+constexpr int COO_LONG = 64;
+constexpr int COO_MAXLONG = COO_TILE / COO_LONG + 2;
+
+__global__ void __launch_bounds__(COO_THREADS)
+coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
+                const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
+                int vec_ok)
+{
+    __shared__ __align__(16) double prod[COO_TILE];
+    __shared__ __align__(16) int srow[COO_TILE];
+    __shared__ int long_start[COO_MAXLONG];
+    __shared__ int n_long;
+
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x;
+    const int t0 = t * COO_TILE;
+    const int n = min(COO_TILE, nnz - t0);
+    const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
+    if (tid == 0) n_long = 0;
+
+    if (n == COO_TILE && vec_ok) {
+#pragma unroll
+        for (int k = 0; k < COO_IPT / 4; k++) {
+            const int o = 4 * (tid + k * COO_THREADS);
+            const int4 r = ld_stream_i4(row + t0 + o, pol_stream);
+            const int4 c = ld_stream_i4(col + t0 + o, pol_stream);
+            const double2 v0 = ld_stream_d2(val + t0 + o, pol_stream), v1 = ld_stream_d2(val + t0 + o + 2, pol_stream);
+            const double x0 = ld_x(x + c.x, pol_x), x1 = ld_x(x + c.y, pol_x), x2 = ld_x(x + c.z, pol_x), x3 = ld_x(x + c.w, pol_x);
+            *reinterpret_cast<int4 *>(srow + o) = r;
+            double2 *dst = reinterpret_cast<double2 *>(prod + o);
+            dst[0] = make_double2(__dmul_rn(v0.x, x0), __dmul_rn(v0.y, x1));
+            dst[1] = make_double2(__dmul_rn(v1.x, x2), __dmul_rn(v1.y, x3));
+        }
+    } else {
+        for (int i = tid; i < n; i += COO_THREADS) {
+            srow[i] = ld_stream_i1(row + t0 + i, pol_stream);
+            prod[i] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream), ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
+        }
+    }
+    const int prev_row = t0 > 0 ? row[t0 - 1] : -1;
+    const bool last_tile = t0 + n == nnz;
+    __syncthreads();
+
+    // ---- one thread per run start among its COO_IPT consecutive entries
+    const int i_begin = tid * COO_IPT, i_end = min(i_begin + COO_IPT, n);
+    for (int i = i_begin; i < i_end; i++) {
+        const int r = srow[i];
+        const int before = i ? srow[i - 1] : prev_row;
+        if (r == before) continue;                              // not a run start
+        for (int e = before + 1; e < r; e++) y[e] = 0.0;        // empty rows in front of this run
+        int j = i + 1;
+        const int stop = min(n, i + COO_LONG + 1);
+        while (j < stop && srow[j] == r) j++;
+        if (j == stop && j < n && srow[j] == r) {               // more than COO_LONG entries in this tile
+            long_start[atomicAdd(&n_long, 1)] = i;
+            continue;
+        }
+        double acc = 0.0;
+        for (int k = i; k < j; k++) acc = __dadd_rn(acc, prod[k]);
+        y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
+    }
+    if (tid == 0 && n > 0 && srow[0] == prev_row) long_start[atomicAdd(&n_long, 1)] = -1;   // carried-in piece
+    if (last_tile && n > 0)
+        for (int e = srow[n - 1] + 1 + tid; e < nRow; e += COO_THREADS) y[e] = 0.0;          // trailing empty rows
+    __syncthreads();
+
+    // ---- one warp per long run / carried-in piece
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int q = warp; q < n_long; q += COO_THREADS / 32) {
+        const int s = long_start[q];
+        const int b = s < 0 ? 0 : s;
+        const int r = srow[b];
+        double acc = 0.0;
+        for (int k = b + lane; k < n && srow[k] == r; k += 32) acc += prod[k];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (s < 0) carry[t] = acc;
+            else y[r] = acc;
+        }
+    }
+}
+
+// one thread per tile: finishes the row whose entries continue from the previous tile (first carrying tile only)
+__global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
+                                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ carry,
+                                 int nnz, int nTiles)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 1 || t >= nTiles) return;
+    const int t0 = t * COO_TILE;
+    const int rc = row[t0];
+    if (row[t0 - 1] != rc) return;                              // a run starts exactly at the tile start
+    const int p0 = t0 - COO_TILE;                               // previous tile: does the run merely pass through it?
+    if (row[p0] == rc && (p0 == 0 ? false : row[p0 - 1] == rc)) return;
+    int b = t0, e = t0;
+    while (b > 0 && t0 - b <= COO_LONG && row[b - 1] == rc) b--;
+    while (e < nnz && e - t0 <= COO_LONG && row[e] == rc) e++;
+    const bool whole = (b == 0 || row[b - 1] != rc) && (e == nnz || row[e] != rc);
+    if (whole && e - b <= COO_LONG) {
+        double acc = 0.0;
+        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn(val[j], x[col[j]]));
+        y[rc] = acc;
+    } else {
+        double sum = 0.0;
+        for (int u = t; u < nTiles && row[u * COO_TILE] == rc; u++) sum += carry[u];
+        y[rc] += sum;
+    }
+}
+
+struct CooFormat : Format {
+    DevBuf<int> row, col;
+    DevBuf<double> val, carry;
+    int nTiles = 0;
+
+    int convert(const CooView &A, cudaStream_t s) override
+    {
+        nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
+        B2_TRY(validate_sorted_coo(A, s));
+        B2_TRY(row.alloc((size_t)nnz));
+        B2_TRY(col.alloc((size_t)nnz));
+        B2_TRY(val.alloc((size_t)nnz));
+        B2_CUDA(cudaMemcpyAsync(row.p, A.row, row.bytes(), cudaMemcpyDeviceToDevice, s));   // opt_coo.cpp:14-19
+        B2_CUDA(cudaMemcpyAsync(col.p, A.col, col.bytes(), cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(cudaMemcpyAsync(val.p, A.val, val.bytes(), cudaMemcpyDeviceToDevice, s));
+        nTiles = ceil_div(nnz, COO_TILE);
+        B2_TRY(carry.alloc((size_t)nTiles));
+        B2_CUDA(cudaStreamSynchronize(s));
+        return B200SPMV_OK;
+    }
+
+    int multiply(const double *x, double *y, cudaStream_t s) override
+    {
+        if (nRow == 0) return B200SPMV_OK;
+        if (nTiles == 0) {
+            B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
+            return B200SPMV_OK;
+        }
+        coo_tile_kernel<<<nTiles, COO_THREADS, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, 1);
+        B2_KERNEL_CHECK();
+        if (nTiles > 1) {
+            coo_fixup_kernel<<<ceil_div(nTiles, 256), 256, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nTiles);
+            B2_KERNEL_CHECK();
+        }
+        return B200SPMV_OK;
+    }
+
+    bool scalar(const std::string &n, long long *out) override
+    {
+        if (n == "alg_bytes") {   // 16 nnz + 8 nCol + 8 nRow
+            *out = 16LL * nnz + 8LL * nCol + 8LL * nRow;
+            return true;
+        }
+        if (n == "launches") { *out = nTiles > 1 ? 2 : 1; return true; }
+        if (n == "nTiles") { *out = nTiles; return true; }
+        return false;
+    }
+
+    long long array(const std::string &n, void *dst, long long cap) override
+    {
+        if (n == "row_idx") return export_device(row.p, row.bytes(), dst, cap);
+        if (n == "col_idx") return export_device(col.p, col.bytes(), dst, cap);
+        if (n == "val") return export_device(val.p, val.bytes(), dst, cap);
+        return -1000;
+    }
+};
+
+Format *make_coo(const b200spmv_options &) { return new CooFormat(); }
+
+}  // namespace b2

@@ -1,15 +1,6 @@
 // stubs.cu -- formats not built yet in this tree state report UNSUPPORTED (never a CPU fallback).
 #include "common.cuh"
 namespace b2 {
-#ifndef HAVE_COO
-Format *make_coo(const b200spmv_options &) { return nullptr; }
-#endif
-#ifndef HAVE_SS
-Format *make_ss(const b200spmv_options &) { return nullptr; }
-#endif
-#ifndef HAVE_CSS
-Format *make_css(const b200spmv_options &) { return nullptr; }
-#endif
 #ifndef HAVE_CSR5
 Format *make_csr5(const b200spmv_options &) { return nullptr; }
 #endif

@@ -146,6 +146,38 @@ def test_ell_golden(sp, name):
     assert np.array_equal(y, g["ell.y"])
 
 
+# ------------------------------------------------------------------------------------------ COO
+def test_coo(sp, oracle, all_cases):
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        A_opt, y = run_host(sp, "coo", nRow, nCol, row, col, val, x)
+        assert np.array_equal(A_opt.array("row_idx", np.int32), row), name      # opt_coo.cpp:14-19 aliases the input
+        assert np.array_equal(A_opt.array("col_idx", np.int32), col), name
+        assert np.array_equal(A_opt.array("val", np.float64), val), name
+        assert A_opt.scalar("alg_bytes") == 16 * len(row) + 8 * nCol + 8 * nRow
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        short = np.bincount(row, minlength=nRow) <= 64
+        assert np.array_equal(y[short], y_ref[short]), name                     # serial order == the verifier's (util.cpp:67-72)
+        assert np.array_equal(y[short], oracle.coo_spmv(nRow, row, col, val, x)[short]), name
+
+
+def test_coo_tile_boundaries(sp, oracle):
+    """Runs that start/end exactly on the 2048-entry tile edges, cross one or several tiles, empty-row gaps."""
+    rng = np.random.default_rng(3)
+    for lens in ([2048, 2048, 1], [2047, 2, 2047, 5000, 0, 0, 3], [1, 0, 4095, 64, 65, 0, 2048 * 3, 7], [10] * 700 + [0] * 50):
+        nRow, nCol = len(lens), 9000
+        row = np.repeat(np.arange(nRow), lens).astype(np.int32)
+        col = np.concatenate([np.sort(rng.choice(nCol, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+        val = rng.standard_normal(len(row))
+        x = rng.random(nCol)
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        for fmt in ("coo", "crs", "ss"):
+            _, y = run_host(sp, fmt, nRow, nCol, row, col, val, x)
+            assert_y(y, y_ref, row, col, val, x, nRow)
+            short = np.array(lens) <= 64
+            assert np.array_equal(y[short], y_ref[short]), (fmt, lens[:4])
+
+
 # ------------------------------------------------------------------------------------------ JDS
 def test_jds(sp, oracle, all_cases):
     for name, nRow, nCol, row, col, val, x in all_cases:
@@ -240,6 +272,74 @@ def test_dia_tma_path_used(sp, oracle):
     nr, nc, r, c, v = oracle.stencil("box3d27", 12)
     A_opt, _ = run_host(sp, "dia", nr, nc, r, c, v, np.ones(nc))
     assert A_opt.scalar("nDiag") == 27 and A_opt.scalar("nRuns") == 9 and A_opt.scalar("tma") == 1
+
+
+# ------------------------------------------------------------------------------------------ SS / CSS
+SS_ARRAYS = ("row_ptr", "row_idx", "col_idx", "segment_index", "sum_segs_count", "sum_segs")
+
+
+def test_ss(sp, oracle, all_cases):
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        for W in (1, 4, 32, 1024):
+            if W > 32 and len(row) < 5000:
+                continue
+            m = oracle.ss_convert(nRow, row, col, val, W)
+            A_opt, y = run_host(sp, "ss", nRow, nCol, row, col, val, x, segment_width=W)
+            assert (A_opt.scalar("H"), A_opt.scalar("nStep"), A_opt.scalar("W")) == (m["H"], m["nStep"], W), (name, W)
+            for k in SS_ARRAYS:
+                assert np.array_equal(A_opt.array(k, np.int32), m[k]), (name, W, k)
+            assert np.array_equal(A_opt.array("val", np.float64), m["val"]), (name, W)
+            assert_y(y, y_ref, row, col, val, x, nRow)                 # fused one-pass multiply
+            short = np.diff(m["row_ptr"]) <= 64
+            assert np.array_equal(y[short], y_ref[short]), (name, W)
+            # three-phase schedule in the reference's operation order: bit-identical to the reference's SS result
+            F_opt, yf = run_host(sp, "ss", nRow, nCol, row, col, val, x, segment_width=W, ss_faithful=1)
+            assert np.array_equal(yf, oracle.ss_spmv(m, x)), (name, W)
+            assert_y(yf, y_ref, row, col, val, x, nRow)
+
+
+@pytest.mark.parametrize("name", GOLD)
+@pytest.mark.parametrize("variant,W", [("ss_opt_w2", 2), ("ss_opt_w4", 4), ("ss_opt_w32", 32)])
+def test_ss_golden(sp, name, variant, W):
+    g = load_golden(name)
+    F_opt, yf = run_host(sp, "ss", int(g["nRow"]), int(g["nCol"]), g["in_row"], g["in_col"], g["in_val"], g["x"],
+                         segment_width=W, ss_faithful=1)
+    assert F_opt.scalar("H") == int(g[variant + ".H"]) and F_opt.scalar("nStep") == int(g[variant + ".nStep"])
+    for k in SS_ARRAYS:
+        assert np.array_equal(F_opt.array(k, np.int32), g["%s.%s" % (variant, k)]), k
+    assert np.array_equal(F_opt.array("val", np.float64), g[variant + ".val"])
+    assert np.array_equal(yf, g[variant + ".y"])                       # the reference's own SS result, bit for bit
+
+
+def test_css(sp, oracle, all_cases):
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        for W, N in ((4, 2), (32, 4), (8, 7)):
+            m = oracle.css_convert(nRow, nCol, row, col, val, W, N)
+            A_opt, y = run_host(sp, "css", nRow, nCol, row, col, val, x, segment_width=W, n_block=N)
+            for k in ("B", "nBlock", "totalH"):
+                assert A_opt.scalar(k) == m[k], (name, W, N, k)
+            for k in ("H", "nStep", "row_ptr", "row_idx", "col_idx", "segment_index", "sum_segs_count", "sum_segs"):
+                assert np.array_equal(A_opt.array(k, np.int32), m[k]), (name, W, N, k)
+            assert np.array_equal(A_opt.array("val", np.float64), m["val"]), (name, W, N)
+            assert_y(y, y_ref, row, col, val, x, nRow)
+            F_opt, yf = run_host(sp, "css", nRow, nCol, row, col, val, x, segment_width=W, n_block=N, ss_faithful=1)
+            assert np.array_equal(yf, oracle.css_spmv(m, x)), (name, W, N)
+
+
+@pytest.mark.parametrize("name", GOLD)
+@pytest.mark.parametrize("variant,W,N", [("css_opt_w2_n2", 2, 2), ("css_opt_w4_n3", 4, 3), ("css_opt_w32_n4", 32, 4)])
+def test_css_golden(sp, name, variant, W, N):
+    g = load_golden(name)
+    F_opt, yf = run_host(sp, "css", int(g["nRow"]), int(g["nCol"]), g["in_row"], g["in_col"], g["in_val"], g["x"],
+                         segment_width=W, n_block=N, ss_faithful=1)
+    for k in ("B", "nBlock", "totalH"):
+        assert F_opt.scalar(k) == int(g["%s.%s" % (variant, k)]), k
+    for k in ("H", "nStep", "row_ptr", "col_idx", "sum_segs_count", "sum_segs"):
+        assert np.array_equal(F_opt.array(k, np.int32), g["%s.%s" % (variant, k)]), k
+    assert np.array_equal(F_opt.array("val", np.float64), g[variant + ".val"])
+    assert np.array_equal(yf, g[variant + ".y"])
 
 
 # ------------------------------------------------------------------------------------------ inputs
