@@ -8,6 +8,13 @@ const char *last_error_cstr();
 }
 using namespace b2;
 
+int b2::xload_mode()
+{
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("B200SPMV_XLOAD"); m = e ? atoi(e) : 0; if (m < 0 || m > 5) m = 0; }
+    return m;
+}
+
 struct b200spmv_matrix {
     int format = 0;
     b200spmv_options opt{};

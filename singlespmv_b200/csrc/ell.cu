@@ -69,7 +69,7 @@ __device__ __forceinline__ void ell_load(EllGroup<V> &g, const int *ecol, const 
 
 // One lane per row; the K-loop runs in ascending slot order with unfused mul/add, i.e. the
 // reference's own order -> y is bit-identical to opt_ell.cpp / opt_crs.cpp.
-template <int V>
+template <int V, int XM>
 __global__ void __launch_bounds__(256)
 ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
                 const double *__restrict__ eval, const double *__restrict__ x, double *__restrict__ y,
@@ -88,9 +88,9 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
         ell_load<V>(b, ecol, eval, ((size_t)(g + 1) * 32 + lane) * V, pol_stream);
         double xa[V], xb[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) xa[j] = ld_x(x + a.c[j], pol_x);
+        for (int j = 0; j < V; j++) xa[j] = ld_x_mode<XM>(x + a.c[j], pol_x);
 #pragma unroll
-        for (int j = 0; j < V; j++) xb[j] = ld_x(x + b.c[j], pol_x);
+        for (int j = 0; j < V; j++) xb[j] = ld_x_mode<XM>(x + b.c[j], pol_x);
 #pragma unroll
         for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
 #pragma unroll
@@ -101,7 +101,7 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
         ell_load<V>(a, ecol, eval, ((size_t)g * 32 + lane) * V, pol_stream);
         double xa[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) xa[j] = ld_x(x + a.c[j], pol_x);
+        for (int j = 0; j < V; j++) xa[j] = ld_x_mode<XM>(x + a.c[j], pol_x);
 #pragma unroll
         for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
     }
@@ -182,8 +182,17 @@ struct EllFormat : Format {
     {
         if (nSlices == 0) return B200SPMV_OK;
         const int blocks = ceil_div((long long)nSlices * 32, 256);
-        if (V == 4) ell_spmv_kernel<4><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices);
-        else ell_spmv_kernel<2><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices);
+#define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices)
+#define ELL_LAUNCH_V(VV)                                   \
+    switch (xload_mode()) {                                \
+    case 1: ELL_LAUNCH(VV, 1); break;                      \
+    case 2: ELL_LAUNCH(VV, 2); break;                      \
+    case 3: ELL_LAUNCH(VV, 3); break;                      \
+    case 4: ELL_LAUNCH(VV, 4); break;                      \
+    case 5: ELL_LAUNCH(VV, 5); break;                      \
+    default: ELL_LAUNCH(VV, 0); break;                     \
+    }
+        if (V == 4) { ELL_LAUNCH_V(4) } else { ELL_LAUNCH_V(2) }
         B2_KERNEL_CHECK();
         return B200SPMV_OK;
     }

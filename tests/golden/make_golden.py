@@ -6,7 +6,8 @@ Inputs : the reference's fixtures /root/reference/matrix/test/{3x3,5x5,10x10,ran
          versions of the five BASELINE.json shapes from oracle/synth_oracle.c.
 Vectors: x = glibc rand() stream seeded with 3, x before y (src/main.cpp:18,31-32).
 Outputs: every SpMatOpt array and the SpMV result y of every reference plugin variant built by
-         oracle/Makefile (oracle/_ref/libref_*.so = unmodified /root/reference/src/opt_*.cpp).
+         oracle/Makefile (oracle/_ref/libref_*.so = unmodified /root/reference/src/opt_*.cpp), and the CSR5
+         arrays (sigma 4 and 16) from the vendored conversion routines (oracle/_ref/libref_csr5.so).
 
     python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
 """
@@ -17,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle_lib import Oracle, RefPlugin, build_oracle  # noqa: E402
+from oracle_lib import Oracle, RefPlugin, build_oracle, ref_csr5_convert  # noqa: E402
 
 VARIANTS = ["crs", "coo", "ell", "jds", "dia", "ss_simple_w4", "ss_opt_w2", "ss_opt_w4", "ss_opt_w32",
             "css_simple_w4_n2", "css_opt_w2_n2", "css_opt_w4_n3", "css_opt_w32_n4"]
@@ -52,6 +53,7 @@ def main():
     cases["mini_box3d27_n3"] = orc.stencil("box3d27", 3)
     cases["mini_uniform_48x8"] = orc.uniform(1, 48, 48, 8)
     cases["mini_rmat_s6"] = orc.rmat(42, 6, 700)
+    cases["mini_rmat_s9"] = orc.rmat(42, 9, 6000)      # empty rows + long rows over many CSR5 tiles
     for name, (nRow, nCol, row, col, val) in cases.items():
         key = row.astype(np.int64) * nCol + col
         assert np.all(np.diff(key) > 0), name + ": not sorted / has duplicates"
@@ -71,6 +73,12 @@ def main():
             for k, a in m.items():
                 out["%s.%s" % (v, k)] = np.asarray(a)
             out["%s.y" % v] = y1
+        # CSR5 arrays from the reference's conversion routines (AVX2 twin at omega = 32, oracle/ref_csr5_shim.cpp)
+        for sigma in (4, 16):
+            m = ref_csr5_convert(nRow, row, col, val, sigma)
+            for k, a in m.items():
+                if k not in ("nRow", "row_ptr"):
+                    out["csr5_s%d.%s" % (sigma, k)] = np.asarray(a)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, nRow, nCol, len(row), "ok")
 

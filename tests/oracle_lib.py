@@ -233,6 +233,48 @@ class Oracle:
                                         buf.ctypes, x.ctypes, y.ctypes)
         return y
 
+    # ---- CSR5 (reference opt/Benchmark_SpMV_using_CSR5, omega = 32; oracle/csr5_oracle.c)
+    def csr5_auto_sigma(self, nRow, nnz):
+        return int(self.lib.orc_csr5_auto_sigma(C.c_int(nRow), C.c_int(nnz)))
+
+    def csr5_convert(self, nRow, row, col, val, sigma=0):
+        row, col, val = _i32(row), _i32(col).copy(), _f64(val).copy()
+        nnz = len(row)
+        if sigma == 0:
+            sigma = self.csr5_auto_sigma(nRow, nnz)
+        ptr = np.empty(nRow + 1, np.int32)
+        self.lib.orc_crs_row_ptr(C.c_int(nRow), C.c_int(nnz), row.ctypes, ptr.ctypes)
+        by, bs, npk, p = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.orc_csr5_shape(C.c_int(nnz), C.c_int(sigma), C.byref(by), C.byref(bs), C.byref(npk), C.byref(p))
+        by, bs, npk, p = by.value, bs.value, npk.value, p.value
+        tile_ptr = np.zeros(p + 1, np.uint32)
+        desc = np.zeros(max(1, p * 32 * npk), np.uint32)
+        off_ptr = np.zeros(p + 1, np.int32)
+        self.lib.orc_csr5_tile_ptr(C.c_int(nRow), C.c_int(nnz), C.c_int(sigma), C.c_int(p), ptr.ctypes, tile_ptr.ctypes)
+        args = (C.c_int(nRow), C.c_int(nnz), C.c_int(sigma), C.c_int(p), C.c_int(by), C.c_int(bs), C.c_int(npk),
+                ptr.ctypes, tile_ptr.ctypes, desc.ctypes, off_ptr.ctypes)
+        n_off = int(self.lib.orc_csr5_descriptor(*args, None))
+        offset = np.zeros(max(1, n_off), np.int32)
+        if n_off:
+            self.lib.orc_csr5_descriptor(*args, offset.ctypes)
+        self.lib.orc_csr5_transpose(C.c_int(nnz), C.c_int(sigma), C.c_int(p), tile_ptr.ctypes, col.ctypes, val.ctypes)
+        return {"sigma": sigma, "p": p, "bit_y_offset": by, "bit_scansum_offset": bs, "num_packet": npk,
+                "num_offsets": n_off, "row_ptr": ptr, "tile_ptr": tile_ptr, "tile_desc": desc[:p * 32 * npk],
+                "tile_desc_offset_ptr": off_ptr, "tile_desc_offset": offset[:n_off], "col_idx": col, "val": val,
+                "nRow": nRow}
+
+    def csr5_spmv(self, m, x):
+        y = np.full(m["nRow"], np.nan)
+        x = _f64(x)
+        desc = m["tile_desc"] if len(m["tile_desc"]) else np.zeros(1, np.uint32)
+        off = m["tile_desc_offset"] if len(m["tile_desc_offset"]) else np.zeros(1, np.int32)
+        self.lib.orc_csr5_spmv(C.c_int(m["nRow"]), C.c_int(len(m["col_idx"])), C.c_int(m["sigma"]), C.c_int(m["p"]),
+                               C.c_int(m["bit_y_offset"]), C.c_int(m["bit_scansum_offset"]), C.c_int(m["num_packet"]),
+                               m["row_ptr"].ctypes, m["tile_ptr"].ctypes, np.ascontiguousarray(desc).ctypes,
+                               m["tile_desc_offset_ptr"].ctypes, np.ascontiguousarray(off).ctypes, m["col_idx"].ctypes,
+                               m["val"].ctypes, x.ctypes, y.ctypes)
+        return y
+
     # ---- reference verifier and vectors (src/util.cpp:67-102, src/main.cpp:18,31-32)
     def verify(self, nRow, row, col, val, x, y):
         row, col, val, x, y = _i32(row), _i32(col), _f64(val), _f64(x), _f64(y)
@@ -346,3 +388,26 @@ class RefPlugin:
         y = np.full(self.nRow, np.nan)       # garbage the plugin must fully overwrite
         self.lib.ref_spmv(y.ctypes)
         return y
+
+
+def ref_csr5_convert(nRow, row, col, val, sigma):
+    """The reference's own CSR5 conversion routines (AVX2 twin, omega = 32): oracle/_ref/libref_csr5.so."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libref_csr5.so"))
+    row, col, val = _i32(row), _i32(col).copy(), _f64(val).copy()
+    nnz = len(row)
+    ptr = np.searchsorted(row, np.arange(nRow + 1), side="left").astype(np.int32)
+    by, bs, npk, p = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib.ref_csr5_shape(C.c_int(nnz), C.c_int(sigma), C.byref(by), C.byref(bs), C.byref(npk), C.byref(p))
+    by, bs, npk, p = by.value, bs.value, npk.value, p.value
+    tile_ptr = np.zeros(p + 1, np.uint32)
+    desc = np.zeros(max(1, p * 32 * npk), np.uint32)
+    off_ptr = np.zeros(p + 1, np.int32)
+    offset = np.zeros(nnz + nRow + 1, np.int32)
+    n_off = C.c_int()
+    err = lib.ref_csr5_convert(C.c_int(nRow), C.c_int(nnz), C.c_int(sigma), ptr.ctypes, col.ctypes, val.ctypes,
+                               tile_ptr.ctypes, desc.ctypes, off_ptr.ctypes, offset.ctypes, C.byref(n_off))
+    assert err == 0
+    return {"sigma": sigma, "p": p, "bit_y_offset": by, "bit_scansum_offset": bs, "num_packet": npk,
+            "num_offsets": n_off.value, "row_ptr": ptr, "tile_ptr": tile_ptr, "tile_desc": desc[:p * 32 * npk],
+            "tile_desc_offset_ptr": off_ptr, "tile_desc_offset": offset[:n_off.value], "col_idx": col, "val": val,
+            "nRow": nRow}
