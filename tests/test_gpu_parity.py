@@ -98,7 +98,9 @@ def test_crs_golden_arrays(sp, name):
     A_opt, y = run_host(sp, "crs", int(g["nRow"]), int(g["nCol"]), g["in_row"], g["in_col"], g["in_val"], g["x"])
     for k, dt in (("ptr", np.int32), ("idx", np.int32), ("val", np.float64)):
         assert np.array_equal(A_opt.array(k, dt), g["crs." + k])
-    assert np.array_equal(y, g["crs.y"])       # all golden rows are short -> exact
+    short = np.diff(g["crs.ptr"]) <= 64        # one thread per row, reference order -> exact
+    assert np.array_equal(y[short], g["crs.y"][short])
+    assert_y(y, g["crs.y"], g["in_row"], g["in_col"], g["in_val"], g["x"], int(g["nRow"]))
 
 
 def test_crs_multiply_rows(sp, oracle):
