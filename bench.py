@@ -219,7 +219,8 @@ def run_single(args, wl, wl_key):
     A = sp.SpMatOpt(fmt, **args.options).convert_device(coo)
     torch.cuda.synchronize()
     t_conv = time.perf_counter() - t0
-    coo.free()
+    if not args.compare_cusparse:
+        coo.free()
     nRow, nCol, nnz = A.nRow, A.nCol, A.nNnz
     alg_bytes = A.scalar("alg_bytes")
     launches_per_step = A.scalar("launches")
@@ -293,6 +294,26 @@ def run_single(args, wl, wl_key):
                     "h2d_bytes_per_step": 8 * nCol, "d2h_bytes_per_step": 8 * nRow},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
 
+    if args.compare_cusparse:
+        # comparison point only (libb200cmp.so, singlespmv_b200/compare/): cusparseSpMV CSR on the same device arrays
+        cmp = C.CDLL(os.path.join(ROOT, "singlespmv_b200", "libb200cmp.so"))
+        cmp.b200cmp_last_error.restype = C.c_char_p
+        res = {}
+        y_c = torch.empty_like(y_d)
+        for alg, name in ((1, "csr_alg1"), (2, "csr_alg2")):
+            ms_c = C.c_float()
+            st = cmp.b200cmp_cusparse_csr(C.c_int(nRow), C.c_int(nCol), C.c_longlong(nnz), C.c_void_p(coo.c.row_d),
+                                          C.c_void_p(coo.c.col_d), C.c_void_p(coo.c.val_d), C.c_void_p(x_d.data_ptr()),
+                                          C.c_void_p(y_c.data_ptr()), alg, args.warmup, args.steps, C.byref(ms_c), sptr)
+            if st != 0:
+                res[name] = {"error": cmp.b200cmp_last_error().decode()}
+                continue
+            torch.cuda.synchronize()
+            rel = float(((y_c - y_d).abs().max() / y_d.abs().max()).item())
+            res[name] = {"ms_per_step": ms_c.value, "gflops": 2.0 * nnz / (ms_c.value * 1e-3) / 1e9, "max_diff_rel_to_max_y": rel}
+        line["cusparse"] = res
+        coo.free()
+
     if not args.no_cpu:
         rows = sample_rows_for(wl, args.mini)
         if wl["kind"] == "rmat":
@@ -322,6 +343,7 @@ def main():
     ap.add_argument("--mini", action="store_true", help="shrunken shapes (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--compare-cusparse", action="store_true", help="also time cusparseSpMV CSR (comparison point)")
     ap.add_argument("--segment-width", type=int, default=0)
     ap.add_argument("--n-block", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=0)

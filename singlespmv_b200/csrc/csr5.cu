@@ -329,6 +329,9 @@ struct Csr5Format : Format {
         B2_TRY(exclusive_scan_i32(cnt.p, offset_ptr.p, p + 1, s));                 // format_avx2.h:262-265
         B2_CUDA(cudaMemcpy(&num_offsets, offset_ptr.p + p, sizeof(int), cudaMemcpyDeviceToHost));
         B2_TRY(offset.alloc((size_t)num_offsets));
+        // every empty-row tile owns one slot more than it has listed segments (its leading partial is never
+        // listed); upstream leaves that slot uninitialised (anonymouslib_avx2.h:178-180), here it is 0
+        B2_CUDA(cudaMemsetAsync(offset.p, 0, offset.bytes() ? offset.bytes() : 4, s));
         if (num_offsets) {
             c5_offset_kernel<<<ceil_div((long long)(p - 1) * 32, 256), 256, 0, s>>>(row_ptr.p, tile_ptr.p, desc.p, offset_ptr.p, offset.p,
                                                                                    sigma, p, bit_y, bit_all, num_packet);

@@ -21,6 +21,7 @@ constexpr int DIA_RPT = 2;
 constexpr int DIA_R = DIA_THREADS * DIA_RPT;
 constexpr int DIA_MAX_DIAG = 64;     // TMA variant: per-diagonal window bases live in shared memory
 constexpr int DIA_MAX_RUNS = 16;
+constexpr int DIA_U = 5;            // diagonals per load round
 
 struct DiaRuns {
     int n;
@@ -114,7 +115,7 @@ __device__ __forceinline__ DiaWindow dia_window(int row0, int off, int cnt, int 
 }
 
 // ---------------------------------------------------------------- multiply, TMA-staged x
-__global__ void __launch_bounds__(DIA_THREADS)
+__global__ void __launch_bounds__(DIA_THREADS, 6)
 dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const DiaRuns runs,
                     const double *__restrict__ x, double *__restrict__ y, int nRow, int nCol)
 {
@@ -169,40 +170,34 @@ dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const
     for (int k = 0; k < DIA_RPT; k++) acc[k] = 0.0;
 
     if (rows == DIA_R) {
-        constexpr int U = 4;
+        // DIA_U x DIA_RPT independent 8-byte loads per thread per round; enough CTAs stay resident
+        // (launch bounds below) that no software double buffer is needed
+        constexpr int U = DIA_U;
         double d[U][DIA_RPT];
         int p = 0;
-        // first batch of diagonal values is in flight while the x windows land
 #pragma unroll
         for (int u = 0; u < U; u++)
 #pragma unroll
             for (int k = 0; k < DIA_RPT; k++)
                 d[u][k] = (u < nDiag) ? ld_stream_d1(dp + (size_t)u * ld + k * DIA_THREADS, pol_stream) : 0.0;
-        mbar_wait(&bar, 0);
-        for (; p + U <= nDiag; p += U) {
-            double dn[U][DIA_RPT];
+        mbar_wait(&bar, 0);                 // the first round of diagonal values is in flight while the x windows land
+        for (;;) {
+            const int m = min(U, nDiag - p);
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (u < m) {
+                    const double *xw = xs + dbase[p + u] + tid;
+#pragma unroll
+                    for (int k = 0; k < DIA_RPT; k++)
+                        acc[k] = __dadd_rn(acc[k], __dmul_rn(d[u][k], xw[k * DIA_THREADS]));
+                }
+            p += U;
+            if (p >= nDiag) break;
 #pragma unroll
             for (int u = 0; u < U; u++)
 #pragma unroll
                 for (int k = 0; k < DIA_RPT; k++)
-                    dn[u][k] = (p + U + u < nDiag) ? ld_stream_d1(dp + (size_t)(p + U + u) * ld + k * DIA_THREADS, pol_stream) : 0.0;
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const double *xw = xs + dbase[p + u] + tid;
-#pragma unroll
-                for (int k = 0; k < DIA_RPT; k++)
-                    acc[k] = __dadd_rn(acc[k], __dmul_rn(d[u][k], xw[k * DIA_THREADS]));
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int k = 0; k < DIA_RPT; k++) d[u][k] = dn[u][k];
-        }
-        for (int u = 0; p + u < nDiag; u++) {
-            const double *xw = xs + dbase[p + u] + tid;
-#pragma unroll
-            for (int k = 0; k < DIA_RPT; k++)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(d[u][k], xw[k * DIA_THREADS]));
+                    d[u][k] = (p + u < nDiag) ? ld_stream_d1(dp + (size_t)(p + u) * ld + k * DIA_THREADS, pol_stream) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < DIA_RPT; k++) y[row0 + tid + k * DIA_THREADS] = acc[k];
