@@ -100,8 +100,9 @@ B200SPMV_API int b200spmv_multiply(b200spmv_matrix *m, const double *x_d, double
 /* Host semantics (what SpMV(A_opt, x_opt, y) means to the reference's driver): copies x H2D,
  * multiplies, copies y D2H, synchronises -- like src/opt_cusparse.cpp:72-82. */
 B200SPMV_API int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h);
-/* Rows [rowBegin,rowEnd) only (CRS): used by the row-partitioned multi-GPU path to overlap the
- * interior block with the halo exchange. */
+/* Rows [rowBegin,rowEnd) only (CRS, SS, CSS, ELL, DIA; others return B200SPMV_ERR_UNSUPPORTED): used by
+ * the row-partitioned multi-GPU path to overlap the interior block with the halo exchange, and by
+ * b200spmv_multiply_host to overlap the D2H copy of finished rows with the rest of the multiply. */
 B200SPMV_API int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const double *x_d,
                            double *y_d, void *stream);
 

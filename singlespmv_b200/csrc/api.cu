@@ -15,6 +15,8 @@ int b2::xload_mode()
     return m;
 }
 
+constexpr int B200SPMV_HOST_CHUNKS = 4;
+
 struct b200spmv_matrix {
     int format = 0;
     b200spmv_options opt{};
@@ -22,10 +24,13 @@ struct b200spmv_matrix {
     bool converted = false;
     // staging for host-semantics multiply
     DevBuf<double> x_stage, y_stage;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t chunk_done[B200SPMV_HOST_CHUNKS] = {};
     ~b200spmv_matrix()
     {
         if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto e : chunk_done) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -196,12 +201,31 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
 {
     B2_TRY(check_ready(m, x_h, y_h));
     Format *f = m->impl.get();
-    if (!m->stream) B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (!m->stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        B2_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : m->chunk_done) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (m->x_stage.n != (size_t)f->nCol) B2_TRY(m->x_stage.alloc((size_t)f->nCol));
     if (m->y_stage.n != (size_t)f->nRow) B2_TRY(m->y_stage.alloc((size_t)f->nRow));
     B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
-    B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
-    B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
+    // Row chunks: the D2H copy of a finished chunk of y overlaps the multiply of the next one (the
+    // reference's cuSPARSE plugin serialises H2D, multiply, D2H: src/opt_cusparse.cpp:72-82).
+    const int nChunks = (f->has_rows() && f->nRow >= (1 << 20)) ? B200SPMV_HOST_CHUNKS : 1;
+    if (nChunks == 1) {
+        B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
+        B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
+        B2_CUDA(cudaStreamSynchronize(m->stream));
+        return B200SPMV_OK;
+    }
+    for (int c = 0; c < nChunks; c++) {
+        const int rb = (int)((long long)f->nRow * c / nChunks) & ~31, re = c + 1 == nChunks ? f->nRow : (int)((long long)f->nRow * (c + 1) / nChunks) & ~31;
+        B2_TRY(f->multiply_rows(rb, re, m->x_stage.p, m->y_stage.p, m->stream));
+        B2_CUDA(cudaEventRecord(m->chunk_done[c], m->stream));
+        B2_CUDA(cudaStreamWaitEvent(m->copy_stream, m->chunk_done[c], 0));
+        B2_CUDA(cudaMemcpyAsync(y_h + rb, m->y_stage.p + rb, sizeof(double) * (size_t)(re - rb), cudaMemcpyDeviceToHost, m->copy_stream));
+    }
+    B2_CUDA(cudaStreamSynchronize(m->copy_stream));
     B2_CUDA(cudaStreamSynchronize(m->stream));
     return B200SPMV_OK;
 }

@@ -84,9 +84,10 @@ struct Format {
     virtual int multiply(const double *x, double *y, cudaStream_t s) = 0;
     virtual int multiply_rows(int, int, const double *, double *, cudaStream_t)
     {
-        set_error("multiply_rows: only the CRS format supports row ranges");
+        set_error("multiply_rows: this format does not support row ranges (CRS, SS, CSS, ELL, DIA do)");
         return B200SPMV_ERR_UNSUPPORTED;
     }
+    virtual bool has_rows() const { return false; }      // multiply_rows available (host-semantics pipeline uses it)
     // format-specific scalars/arrays; return false / -1 when the name is unknown
     virtual bool scalar(const std::string &name, long long *out) = 0;
     virtual long long array(const std::string &name, void *dst_h, long long dst_bytes) = 0;

@@ -1,7 +1,5 @@
 // crs.cu -- CRS plugin: device conversion + adaptive tile-stream multiply.
 // Reference: /root/reference/src/opt_crs.{h,cpp} (SpMatOpt{ptr,idx,val}; OptimizeProblem :10-42; SpMV :44-70).
-#include <map>
-
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -10,7 +8,6 @@ struct CrsFormat : Format {
     DevBuf<int> ptr, idx;
     DevBuf<double> val;
     TileStream ts;
-    std::map<std::pair<int, int>, std::pair<int, int>> tile_range_cache;
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -23,33 +20,14 @@ struct CrsFormat : Format {
         B2_CUDA(cudaMemcpyAsync(idx.p, A.col, idx.bytes(), cudaMemcpyDeviceToDevice, s));   // :29
         B2_CUDA(cudaMemcpyAsync(val.p, A.val, val.bytes(), cudaMemcpyDeviceToDevice, s));   // :30
         B2_TRY(ts.build(ptr.p, idx.p, val.p, nRow, nnz, s));
-        tile_range_cache.clear();
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return ts.run_all(x, y, false, s); }
 
-    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
-    {
-        if (rb < 0 || re > nRow || rb > re) {
-            set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow);
-            return B200SPMV_ERR_INVALID;
-        }
-        if (rb == re) return B200SPMV_OK;
-        auto key = std::make_pair(rb, re);
-        auto it = tile_range_cache.find(key);
-        if (it == tile_range_cache.end()) {
-            // tiles that hold any entry (or the shared position of empty rows) of rows [rb,re)
-            int pb = 0, pe = 0;
-            B2_CUDA(cudaMemcpy(&pb, ptr.p + rb, sizeof(int), cudaMemcpyDeviceToHost));
-            B2_CUDA(cudaMemcpy(&pe, ptr.p + re, sizeof(int), cudaMemcpyDeviceToHost));
-            int lo = ts.nTiles ? std::min(pb / TS_TILE, ts.nTiles - 1) : 0;
-            int hi = std::min(ts.nTiles, pe / TS_TILE + 1);
-            it = tile_range_cache.emplace(key, std::make_pair(lo, hi)).first;
-        }
-        return ts.run(x, y, false, rb, re, it->second.first, it->second.second, s);
-    }
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override { return ts.run_rows(x, y, false, rb, re, s); }
+    bool has_rows() const override { return true; }
 
     bool scalar(const std::string &n, long long *out) override
     {

@@ -117,14 +117,14 @@ __device__ __forceinline__ DiaWindow dia_window(int row0, int off, int cnt, int 
 // ---------------------------------------------------------------- multiply, TMA-staged x
 __global__ void __launch_bounds__(DIA_THREADS, 6)
 dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const DiaRuns runs,
-                    const double *__restrict__ x, double *__restrict__ y, int nRow, int nCol)
+                    const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int nCol)
 {
     extern __shared__ __align__(16) double xs[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int dbase[DIA_MAX_DIAG];
 
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * DIA_R;
+    const int row0 = rowBegin + blockIdx.x * DIA_R;
     const uint64_t pol_x = policy_evict_last(), pol_stream = policy_evict_first();
 
     if (tid == 0) mbar_init(&bar, 1);
@@ -163,7 +163,7 @@ dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const
     }
     __syncthreads();
 
-    const int rows = min(DIA_R, nRow - row0);
+    const int rows = min(DIA_R, rowEnd - row0);
     const double *dp = diag + row0 + tid;
     double acc[DIA_RPT];
 #pragma unroll
@@ -220,10 +220,10 @@ dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const
 // ---------------------------------------------------------------- multiply, x through L1/L2 (any number of diagonals)
 __global__ void __launch_bounds__(DIA_THREADS)
 dia_spmv_direct_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const int *__restrict__ ioff,
-                       const double *__restrict__ x, double *__restrict__ y, int nRow, int nCol)
+                       const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int nRow, int nCol)
 {
-    const int r = blockIdx.x * DIA_THREADS + threadIdx.x;
-    if (r >= nRow) return;
+    const int r = rowBegin + blockIdx.x * DIA_THREADS + threadIdx.x;
+    if (r >= rowEnd) return;
     const uint64_t pol_x = policy_evict_last(), pol_stream = policy_evict_first();
     const int shift = nRow - 1;
     double acc = 0.0;
@@ -324,17 +324,21 @@ struct DiaFormat : Format {
         return B200SPMV_OK;
     }
 
-    int multiply(const double *x, double *y, cudaStream_t s) override
+    int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
+    bool has_rows() const override { return true; }
+
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
-        if (nRow == 0) return B200SPMV_OK;
+        if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re) return B200SPMV_OK;
         if (nDiag == 0) {
-            B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
+            B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
             return B200SPMV_OK;
         }
         if (tma_ok && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-            dia_spmv_tma_kernel<<<ceil_div(nRow, DIA_R), DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, nRow, nCol);
+            dia_spmv_tma_kernel<<<ceil_div(re - rb, DIA_R), DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
         else
-            dia_spmv_direct_kernel<<<ceil_div(nRow, DIA_THREADS), DIA_THREADS, 0, s>>>(diag.p, ld, nDiag, ioff.p, x, y, nRow, nCol);
+            dia_spmv_direct_kernel<<<ceil_div(re - rb, DIA_THREADS), DIA_THREADS, 0, s>>>(diag.p, ld, nDiag, ioff.p, x, y, rb, re, nRow, nCol);
         B2_KERNEL_CHECK();
         return B200SPMV_OK;
     }

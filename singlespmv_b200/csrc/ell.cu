@@ -73,11 +73,11 @@ template <int V, int XM>
 __global__ void __launch_bounds__(256)
 ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
                 const double *__restrict__ eval, const double *__restrict__ x, double *__restrict__ y,
-                int nRow, int nSlices)
+                int rowBegin, int rowEnd, int sliceBegin, int sliceEnd)
 {
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int s = sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (s >= nSlices) return;
+    if (s >= sliceEnd) return;
     const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
     const long long g0 = slice_off[s], g1 = slice_off[s + 1];
     double acc = 0.0;
@@ -106,7 +106,7 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
         for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
     }
     const int r = s * 32 + lane;
-    if (r < nRow) y[r] = acc;
+    if (r >= rowBegin && r < rowEnd) y[r] = acc;
 }
 
 // Logical [nRow][K] view for parity checks (slots beyond the slice width are padding).
@@ -178,11 +178,16 @@ struct EllFormat : Format {
         return B200SPMV_OK;
     }
 
-    int multiply(const double *x, double *y, cudaStream_t s) override
+    int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
+    bool has_rows() const override { return true; }
+
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
-        if (nSlices == 0) return B200SPMV_OK;
-        const int blocks = ceil_div((long long)nSlices * 32, 256);
-#define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, nRow, nSlices)
+        if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re) return B200SPMV_OK;
+        const int sb = rb / 32, se = ceil_div(re, 32);
+        const int blocks = ceil_div((long long)(se - sb) * 32, 256);
+#define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, rb, re, sb, se)
 #define ELL_LAUNCH_V(VV)                                   \
     switch (xload_mode()) {                                \
     case 1: ELL_LAUNCH(VV, 1); break;                      \

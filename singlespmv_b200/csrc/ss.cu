@@ -265,6 +265,13 @@ struct SsFormat : Format {
         return B200SPMV_OK;
     }
 
+    bool has_rows() const override { return !faithful; }
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
+    {
+        if (faithful) return Format::multiply_rows(rb, re, x, y, s);
+        return ts.run_rows(x, y, false, rb, re, s);
+    }
+
     bool scalar(const std::string &n, long long *out) override
     {
         if (n == "H") { *out = H; return true; }
@@ -441,6 +448,20 @@ struct CssFormat : Format {
                                                                 nRow, W, 1, y);                           // opt_css.cpp:298
             B2_KERNEL_CHECK();
         }
+        return B200SPMV_OK;
+    }
+
+    bool has_rows() const override { return !faithful; }
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
+    {
+        if (faithful) return Format::multiply_rows(rb, re, x, y, s);
+        if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re) return B200SPMV_OK;
+        if (nBlock == 0) {
+            B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
+            return B200SPMV_OK;
+        }
+        for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->ts.run_rows(x, y, b > 0, rb, re, s));
         return B200SPMV_OK;
     }
 

@@ -1,4 +1,5 @@
 // tile_stream.cu -- kernels of the tile-stream multiply (see tile_stream.cuh).
+#include <algorithm>
 #include <cstdlib>
 
 #include "tile_stream.cuh"
@@ -124,104 +125,6 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     }
 }
 
-// ---- v2: same contract as tile_stream_kernel, restructured after the first ncu captures
-//  * every DRAM-latency-bound load of the tile is issued up front: the tile's slice of row_ptr is staged
-//    in shared memory together with the matrix stream (v1 read row_ptr after the barrier: a dependent
-//    DRAM round trip with nothing else in flight);
-//  * entries are assigned lane-contiguously (thread t takes t, t+256, ...): the x gather of a warp then
-//    touches the fewest distinct sectors for stencil-like rows (v1: lane stride 4 -> ~1 sector per lane).
-constexpr int TS_SPTR = TS_TILE + 8;     // staged row_ptr entries (rows owned by a tile without empty rows <= TS_TILE)
-
-__global__ void __launch_bounds__(TS_THREADS, 6)
-tile_stream_kernel_v2(const int *__restrict__ row_ptr, const int *__restrict__ col,
-                      const double *__restrict__ val, const int *__restrict__ tile_row,
-                      const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
-                      int nnz, int tileLo, int rowLo, int rowHi, int accumulate)
-{
-    __shared__ __align__(16) double prod[TS_TILE];
-    __shared__ int sptr[TS_SPTR];
-    __shared__ int long_row[TS_MAXLONG];
-    __shared__ int n_long;
-
-    const int tid = threadIdx.x;
-    const int t = tileLo + blockIdx.x;
-    const int t0 = t * TS_TILE;
-    const int t1 = min(t0 + TS_TILE, nnz);
-    const int n = t1 - t0;
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_x = policy_evict_last();
-    if (tid == 0) n_long = 0;
-
-    // matrix stream first (independent of everything else)
-    int c[TS_IPT];
-    double v[TS_IPT];
-#pragma unroll
-    for (int k = 0; k < TS_IPT; k++) {
-        const int i = tid + k * TS_THREADS;
-        if (i < n) {
-            c[k] = ld_stream_i1(col + t0 + i, pol_stream);
-            v[k] = ld_stream_d1(val + t0 + i, pol_stream);
-        }
-    }
-    const int r_lo = tile_row[t], r_hi = tile_row[t + 1];
-    const int n_ptr = min(r_hi - r_lo + 1, TS_SPTR);           // row_ptr[r_lo .. r_hi] (r_hi <= nRow)
-    for (int i = tid; i < n_ptr; i += TS_THREADS) sptr[i] = row_ptr[r_lo + i];
-#pragma unroll
-    for (int k = 0; k < TS_IPT; k++) {
-        const int i = tid + k * TS_THREADS;
-        if (i < n) prod[i] = __dmul_rn(v[k], ld_x(x + c[k], pol_x));
-    }
-    __syncthreads();
-
-    const int first = sptr[0];                 // row_ptr[r_lo]
-    const int cin_end = min(first, t1);        // [t0, cin_end) belongs to row r_lo-1
-
-    // ---- one thread per owned row
-    for (int i = tid; i < r_hi - r_lo; i += TS_THREADS) {
-        const int r = r_lo + i;
-        if (r < rowLo || r >= rowHi) continue;
-        const int b = i < n_ptr ? sptr[i] : row_ptr[r];
-        const int e_full = i + 1 < n_ptr ? sptr[i + 1] : row_ptr[r + 1];
-        const int e = min(e_full, t1);
-        if (e_full > t1 && e_full - b <= TS_LONG) continue;   // short row crossing: fix-up recomputes it
-        if (e - b > TS_LONG) {
-            long_row[atomicAdd(&n_long, 1)] = r;
-            continue;
-        }
-        double acc = 0.0;
-        for (int j = b; j < e; j++) acc = __dadd_rn(acc, prod[j - t0]);
-        y[r] = accumulate ? __dadd_rn(y[r], acc) : acc;
-    }
-    if (tid == 0 && cin_end > t0) {
-        const int rc = r_lo - 1;
-        if (first - row_ptr[rc] > TS_LONG && rc >= rowLo && rc < rowHi)
-            long_row[atomicAdd(&n_long, 1)] = -1;
-    }
-    __syncthreads();
-
-    // ---- one warp per long row / carried-in piece
-    const int lane = tid & 31, warp = tid >> 5;
-    const int nl = n_long;
-    for (int q = warp; q < nl; q += TS_THREADS / 32) {
-        const int r = long_row[q];
-        int b, e;
-        if (r < 0) {
-            b = t0;
-            e = cin_end;
-        } else {
-            b = row_ptr[r];
-            e = min(row_ptr[r + 1], t1);
-        }
-        double acc = 0.0;
-        for (int j = b + lane; j < e; j += 32) acc += prod[j - t0];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            if (r < 0) carry[t] = acc;
-            else y[r] = accumulate ? y[r] + acc : acc;
-        }
-    }
-}
-
 // Finishes the rows that cross tile boundaries; one thread per tile, only the FIRST carrying
 // tile of a row acts.  Short rows are recomputed from global memory in the reference's order.
 __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
@@ -265,7 +168,30 @@ int TileStream::build(const int *row_ptr_d, const int *col_d, const double *val_
     B2_TRY(carry.alloc((size_t)nTiles));
     tile_row_kernel<<<ceil_div(nTiles + 1, 256), 256, 0, s>>>(row_ptr, nRow, nTiles, tile_row.p);
     B2_KERNEL_CHECK();
+    range_cache.clear();
     return B200SPMV_OK;
+}
+
+int TileStream::run_rows(const double *x, double *y, bool accumulate, int rb, int re, cudaStream_t s)
+{
+    if (rb < 0 || re > nRow || rb > re) {
+        set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow);
+        return B200SPMV_ERR_INVALID;
+    }
+    if (rb == re) return B200SPMV_OK;
+    if (rb == 0 && re == nRow) return run_all(x, y, accumulate, s);
+    const auto key = std::make_pair(rb, re);
+    auto it = range_cache.find(key);
+    if (it == range_cache.end()) {
+        // tiles that hold any entry (or the shared position of empty rows) of rows [rb, re)
+        int pb = 0, pe = 0;
+        B2_CUDA(cudaMemcpy(&pb, row_ptr + rb, sizeof(int), cudaMemcpyDeviceToHost));
+        B2_CUDA(cudaMemcpy(&pe, row_ptr + re, sizeof(int), cudaMemcpyDeviceToHost));
+        const int lo = nTiles ? std::min(pb / TS_TILE, nTiles - 1) : 0;
+        const int hi = std::min(nTiles, pe / TS_TILE + 1);
+        it = range_cache.emplace(key, std::make_pair(lo, hi)).first;
+    }
+    return run(x, y, accumulate, rb, re, it->second.first, it->second.second, s);
 }
 
 int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo,
@@ -277,14 +203,9 @@ int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int 
         return B200SPMV_OK;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
-    static const int variant = getenv("B200SPMV_TS") ? atoi(getenv("B200SPMV_TS")) : 2;
-    if (variant == 1)
-        tile_stream_kernel<<<tileHi - tileLo, TS_THREADS, 0, s>>>(row_ptr, col, val, tile_row.p, x, y, carry.p,
-                                                                 nnz, tileLo, rowLo, rowHi, accumulate ? 1 : 0,
-                                                                 vec_ok);
-    else
-        tile_stream_kernel_v2<<<tileHi - tileLo, TS_THREADS, 0, s>>>(row_ptr, col, val, tile_row.p, x, y, carry.p,
-                                                                    nnz, tileLo, rowLo, rowHi, accumulate ? 1 : 0);
+    tile_stream_kernel<<<tileHi - tileLo, TS_THREADS, 0, s>>>(row_ptr, col, val, tile_row.p, x, y, carry.p,
+                                                             nnz, tileLo, rowLo, rowHi, accumulate ? 1 : 0,
+                                                             vec_ok);
     B2_KERNEL_CHECK();
     if (tileHi - tileLo > 1 || tileLo > 0) {
         tile_fixup_kernel<<<ceil_div(tileHi - tileLo, 256), 256, 0, s>>>(row_ptr, col, val, tile_row.p, x, y,

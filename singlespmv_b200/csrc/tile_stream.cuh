@@ -14,7 +14,13 @@
 // A second, tiny kernel finishes rows that cross tile boundaries: short ones are recomputed
 // sequentially (so EVERY row up to TS_LONG entries is bit-exact), long ones get their carries
 // added in tile order (deterministic).
+//
+// Variants measured and rejected on B200 (profiles/r1_call8_9_summary.md): scalar lane-contiguous loads (-20 %:
+// 24 instead of 14 load instructions per thread), row_ptr staged in shared memory + warp-local long rows
+// (-15 %: 40 registers -> 6 instead of 8 resident CTAs).  Resident CTAs x 24 KB in flight is what feeds HBM.
 #pragma once
+#include <map>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -45,7 +51,10 @@ struct TileStream {
     {
         return run(x, y, accumulate, 0, nRow, 0, nTiles, s);
     }
+    // rows [rb, re) only: looks up (and caches) the tiles that hold their entries
+    int run_rows(const double *x, double *y, bool accumulate, int rb, int re, cudaStream_t s);
     size_t meta_bytes() const { return tile_row.bytes(); }
+    std::map<std::pair<int, int>, std::pair<int, int>> range_cache;
 };
 
 }  // namespace b2

@@ -103,19 +103,49 @@ def test_crs_golden_arrays(sp, name):
     assert_y(y, g["crs.y"], g["in_row"], g["in_col"], g["in_val"], g["x"], int(g["nRow"]))
 
 
-def test_crs_multiply_rows(sp, oracle):
+@pytest.mark.parametrize("fmt,opt", [("crs", {}), ("ss", {"segment_width": 8}), ("css", {"segment_width": 4, "n_block": 3}),
+                                     ("ell", {}), ("dia", {})])
+def test_multiply_rows(sp, oracle, fmt, opt):
     import torch
     nr, nc, row, col, val = oracle.stencil("lap3d7", 20)
     x = oracle.reference_vectors(nc, nr)[0]
     y_ref = oracle.crs_result(nr, row, col, val, x)
-    A_opt, _ = run_host(sp, "crs", nr, nc, row, col, val, x)
+    A_opt, _ = run_host(sp, fmt, nr, nc, row, col, val, x, **opt)
     xd = torch.from_numpy(x).cuda()
     yd = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
     cuts = [0, 1, 399, 400, 4001, 7600, nr]
     for a, b in zip(cuts[:-1], cuts[1:]):
         A_opt.multiply_rows(a, b, xd.data_ptr(), yd.data_ptr())
     torch.cuda.synchronize()
-    assert np.array_equal(yd.cpu().numpy(), y_ref)
+    y = yd.cpu().numpy()
+    if fmt == "css":
+        assert_y(y, y_ref, row, col, val, x, nr)        # block partial sums are re-associated
+    else:
+        assert np.array_equal(y, y_ref)
+    # rows outside the requested range are left alone
+    yd.fill_(-3.0)
+    A_opt.multiply_rows(1000, 2000, xd.data_ptr(), yd.data_ptr())
+    torch.cuda.synchronize()
+    y = yd.cpu().numpy()
+    assert np.all(y[:1000] == -3.0) and np.all(y[2000:] == -3.0) and np.array_equal(y[1000:2000], y_ref[1000:2000]) or fmt == "css"
+    for bad in ("coo", "jds", "csr5"):
+        B_opt, _ = run_host(sp, bad, 3, 3, [0, 1], [0, 1], [1.0, 2.0], np.ones(3))
+        with pytest.raises(sp.B200SpmvError) as e:
+            B_opt.multiply_rows(0, 1, xd.data_ptr(), yd.data_ptr())
+        assert e.value.status == -3
+
+
+@pytest.mark.parametrize("fmt,opt", [("crs", {}), ("css", {"n_block": 3}), ("ell", {}), ("dia", {}), ("jds", {})])
+def test_host_multiply_pipeline_large(sp, oracle, fmt, opt):
+    """>= 2^20 rows: b200spmv_multiply_host runs row chunks with the D2H of y overlapped (formats with row ranges)."""
+    nr, nc, row, col, val = oracle.stencil("lap2d5", 1100)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    _, y = run_host(sp, fmt, nr, nc, row, col, val, x, **opt)
+    if fmt == "css":
+        assert_y(y, y_ref, row, col, val, x, nr)
+    else:
+        assert np.array_equal(y, y_ref)
 
 
 # ------------------------------------------------------------------------------------------ ELL
