@@ -8,7 +8,7 @@ Metric: SpMV GFLOP/s = 2 nnz / t (src/main.cpp:196), with effective HBM GB/s (co
 in `roofline`.  Workloads are BASELINE.json's configs:
 
     c1  2-D 5-point Laplacian 1024^2, CRS            c4  3-D 27-point 256^3, DIA
-    c2  uniform random 2^24 rows x 32/row, ELL       c5  3-D 7-point 512^3, row-partitioned CRS
+    c2  uniform random 2^24 rows x 32/row, CSS(3)    c5  3-D 7-point 512^3, row-partitioned CRS
     c3  R-MAT scale 23, 2^28 draws, CRS
 
 N = 1 defaults to c2 (the config the metric is quoted on that fits one GPU); N > 1 defaults to c5, the
@@ -37,8 +37,9 @@ L2_BYTES = 126 * 1024 * 1024
 WORKLOADS = {
     "c1": dict(kind="lap2d5", p0=1024, p1=0, seed=1, fmt="crs",
                name="CRS fp64, 2-D 5-point Laplacian 1024x1024 (1,048,576 rows, 5,238,784 nnz)"),
-    "c2": dict(kind="uniform", p0=1 << 24, p1=32, seed=1, fmt="ell",
-               name="sliced-ELL fp64, uniform random 16,777,216 rows x 32 nnz/row (536,870,912 nnz)"),
+    "c2": dict(kind="uniform", p0=1 << 24, p1=32, seed=1, fmt="css", opts=dict(n_block=3), also=["ss", "ell", "jds"],
+               name="SS family (column-blocked SS = CSS, N_BLOCK=3; SS / sliced-ELL / JDS in `formats`) fp64, "
+                    "uniform random 16,777,216 rows x 32 nnz/row (536,870,912 nnz)"),
     "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="crs",
                name="adaptive CRS fp64, R-MAT scale 23, 2^28 edge draws (duplicates removed)"),
     "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia",
@@ -216,10 +217,16 @@ def run_single(args, wl, wl_key):
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    A = sp.SpMatOpt(fmt, **args.options).convert_device(coo)
+    options = dict(args.options)
+    if not args.format:                      # the workload's own tunables apply to its default format only
+        for k, v in wl.get("opts", {}).items():
+            if not options.get(k):
+                options[k] = v
+    A = sp.SpMatOpt(fmt, **options).convert_device(coo)
     torch.cuda.synchronize()
     t_conv = time.perf_counter() - t0
-    if not args.compare_cusparse:
+    also = [] if (args.format or args.no_also) else list(wl.get("also", []))
+    if not args.compare_cusparse and not also:
         coo.free()
     nRow, nCol, nnz = A.nRow, A.nCol, A.nNnz
     alg_bytes = A.scalar("alg_bytes")
@@ -283,7 +290,7 @@ def run_single(args, wl, wl_key):
     line = {"metric": "SpMV GFLOP/s", "value": gflops, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "nRow": nRow, "nCol": nCol, "nnz": nnz,
+            "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "options": {k: v for k, v in options.items() if v}, "nRow": nRow, "nCol": nCol, "nnz": nnz,
                        "x": "srand(3) rand()/RAND_MAX (src/main.cpp:18,31)",
                        "l2": "flushed between steps (512 MiB write)" if need_flush else "inputs larger than L2 (%.2f GB streamed per step)" % (alg_bytes / 1e9),
                        "convert_ms": t_conv * 1e3, "generate_ms": t_gen * 1e3},
@@ -293,6 +300,27 @@ def run_single(args, wl, wl_key):
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": 8 * nCol, "d2h_bytes_per_step": 8 * nRow},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+
+    if also:
+        # the other formats BASELINE.json names for this config: same matrix, same x, short device-resident runs
+        line["formats"] = {fmt: {"gflops": gflops, "ms_per_step": ms, "frac": achieved / peak}}
+        for f2 in also:
+            B = sp.SpMatOpt(f2).convert_device(coo)
+            for _ in range(3):
+                B.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n2 = max(3, args.steps // 5)
+            ea.record(stream)
+            for _ in range(n2):
+                B.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr)
+            eb.record(stream)
+            torch.cuda.synchronize()
+            ms2 = ea.elapsed_time(eb) / n2
+            line["formats"][f2] = {"gflops": 2.0 * nnz / (ms2 * 1e-3) / 1e9, "ms_per_step": ms2,
+                                   "frac": B.scalar("alg_bytes") / (ms2 * 1e-3) / 1e9 / peak}
+            B.destroy()
+        if not args.compare_cusparse:
+            coo.free()
 
     if args.compare_cusparse:
         # comparison point only (libb200cmp.so, singlespmv_b200/compare/): cusparseSpMV CSR on the same device arrays
@@ -343,6 +371,8 @@ def main():
     ap.add_argument("--mini", action="store_true", help="shrunken shapes (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of the config's other formats")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch each step eagerly instead of one CUDA graph")
     ap.add_argument("--compare-cusparse", action="store_true", help="also time cusparseSpMV CSR (comparison point)")
     ap.add_argument("--segment-width", type=int, default=0)
     ap.add_argument("--n-block", type=int, default=0)

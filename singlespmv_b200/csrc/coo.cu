@@ -60,22 +60,21 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
     const bool last_tile = t0 + n == nnz;
     __syncthreads();
 
-    // ---- one thread per run start among its COO_IPT consecutive entries
-    const int i_begin = tid * COO_IPT, i_end = min(i_begin + COO_IPT, n);
-    for (int i = i_begin; i < i_end; i++) {
+    // ---- one thread per run start; entries are examined lane-contiguously (conflict-free shared reads)
+#pragma unroll 1
+    for (int i = tid; i < n; i += COO_THREADS) {
         const int r = srow[i];
         const int before = i ? srow[i - 1] : prev_row;
         if (r == before) continue;                              // not a run start
         for (int e = before + 1; e < r; e++) y[e] = 0.0;        // empty rows in front of this run
-        int j = i + 1;
         const int stop = min(n, i + COO_LONG + 1);
-        while (j < stop && srow[j] == r) j++;
+        double acc = 0.0;
+        int j = i;
+        for (; j < stop && srow[j] == r; j++) acc = __dadd_rn(acc, prod[j]);
         if (j == stop && j < n && srow[j] == r) {               // more than COO_LONG entries in this tile
             long_start[atomicAdd(&n_long, 1)] = i;
             continue;
         }
-        double acc = 0.0;
-        for (int k = i; k < j; k++) acc = __dadd_rn(acc, prod[k]);
         y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
     }
     if (tid == 0 && n > 0 && srow[0] == prev_row) long_start[atomicAdd(&n_long, 1)] = -1;   // carried-in piece

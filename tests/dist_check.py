@@ -1,0 +1,64 @@
+"""Multi-GPU parity check, run under torchrun on a box with >= 2 GPUs (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+
+Every rank multiplies its row block with the NCCL halo exchange (singlespmv_b200.dist.DistSpmv); rank 0
+also multiplies the whole matrix on its own GPU with the single-GPU CRS path.  The blocks are renumbered
+monotonically, so the concatenated y must be bit-identical."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import singlespmv_b200 as sp                      # noqa: E402
+from singlespmv_b200.dist import DistSpmv         # noqa: E402
+
+
+def main():
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ok = True
+    for kind, p0, p1 in (("lap3d7", 96, 0), ("box3d27", 48, 0), ("lap2d5", 700, 0), ("uniform", 1 << 16, 16)):
+        eng = DistSpmv(kind, p0, p1, 1)
+        n = int(eng.bounds[-1])
+        x_h, _ = sp.reference_vectors(n, 0, 3)
+        lo, hi = int(eng.bounds[rank]), int(eng.bounds[rank + 1])
+        eng.block.x_owned.copy_(torch.from_numpy(x_h[lo:hi]))
+        for _ in range(3):                       # repeated steps must be idempotent
+            eng.step()
+        graphed = eng.enable_graph() if os.environ.get("DIST_CHECK_GRAPH", "1") == "1" else False
+        eng.block.y.fill_(float("nan"))
+        for _ in range(2):
+            eng.step()
+        torch.cuda.synchronize()
+        sizes = [int(eng.bounds[r + 1] - eng.bounds[r]) for r in range(world)]
+        parts = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
+        dist.all_gather(parts, eng.block.y)
+        if rank == 0:
+            y = torch.cat(parts)
+            coo = sp.DeviceCoo(kind, p0, p1, 1)
+            A = sp.SpMatOpt("crs").convert_device(coo)
+            xd = torch.from_numpy(x_h).cuda()
+            y1 = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+            A.multiply(xd.data_ptr(), y1.data_ptr())
+            torch.cuda.synchronize()
+            same = bool(torch.equal(y, y1))
+            halo = eng.block.nLeft + eng.block.nRight
+            print("dist_check %s p0=%d world=%d rows=%d halo(rank0)=%d interior(rank0)=[%d,%d) bit-identical=%s graph=%s %s"
+                  % (kind, p0, world, n, halo, eng.block.interiorBegin, eng.block.interiorEnd, same, graphed,
+                     eng.graph_error or ""), flush=True)
+            ok = ok and same
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
