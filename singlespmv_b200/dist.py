@@ -242,6 +242,11 @@ class DistSpmv:
                 pass
         return self.graph is not None
 
+    def release_graph(self):
+        import gc
+        self.graph = None
+        gc.collect()
+
     def step(self):
         if self.graph is not None:
             self.graph.replay()
@@ -360,4 +365,10 @@ def run_partitioned_bench(args, wl, wl_key):
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     dist.barrier()
-    dist.destroy_process_group()
+    eng.release_graph()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # a captured NCCL graph can keep ncclCommDestroy waiting at interpreter teardown (seen on 2 x B200, torch 2.11 /
+    # NCCL 2.28.9): everything is flushed and every rank has passed the barrier, so leave without the destructors
+    os._exit(0)

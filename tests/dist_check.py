@@ -54,10 +54,16 @@ def main():
                      eng.graph_error or ""), flush=True)
             ok = ok and same
         dist.barrier()
+        eng.release_graph()
+        torch.cuda.synchronize()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    code = 0 if int(flag.item()) == 1 else 1
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)        # see singlespmv_b200/dist.py: teardown with captured NCCL graphs can hang
 
 
 if __name__ == "__main__":
