@@ -27,17 +27,19 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
 {
     __shared__ __align__(16) double prod[COO_TILE];
     __shared__ __align__(16) int srow[COO_TILE];
+    __shared__ unsigned head[COO_TILE / 32 + 1];     // bit i = entry i starts a run of equal row ids
     __shared__ int long_start[COO_MAXLONG];
     __shared__ int n_long;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int t = blockIdx.x;
     const int t0 = t * COO_TILE;
     const int n = min(COO_TILE, nnz - t0);
     const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
     if (tid == 0) n_long = 0;
+    const bool fast = n == COO_TILE && vec_ok;
 
-    if (n == COO_TILE && vec_ok) {
+    if (fast) {
 #pragma unroll
         for (int k = 0; k < COO_IPT / 4; k++) {
             const int o = 4 * (tid + k * COO_THREADS);
@@ -49,8 +51,19 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
             double2 *dst = reinterpret_cast<double2 *>(prod + o);
             dst[0] = make_double2(__dmul_rn(v0.x, x0), __dmul_rn(v0.y, x1));
             dst[1] = make_double2(__dmul_rn(v1.x, x2), __dmul_rn(v1.y, x3));
+            // run starts, in registers: the row id in front of this lane's four entries comes from the lane below
+            int prev = __shfl_up_sync(0xffffffffu, r.w, 1);
+            if (lane == 0) prev = (t0 + o) > 0 ? row[t0 + o - 1] : -1;
+            unsigned bits = (unsigned)(r.x != prev) | ((unsigned)(r.y != r.x) << 1) | ((unsigned)(r.z != r.y) << 2) |
+                            ((unsigned)(r.w != r.z) << 3);
+            bits <<= 4 * (lane & 7);                           // eight lanes share one 32-entry word
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+            bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+            if ((lane & 7) == 0) head[o >> 5] = bits;
         }
     } else {
+        for (int i = tid; i < COO_TILE / 32 + 1; i += COO_THREADS) head[i] = 0u;
         for (int i = tid; i < n; i += COO_THREADS) {
             srow[i] = ld_stream_i1(row + t0 + i, pol_stream);
             prod[i] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream), ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
@@ -59,23 +72,38 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
     const int prev_row = t0 > 0 ? row[t0 - 1] : -1;
     const bool last_tile = t0 + n == nnz;
     __syncthreads();
+    if (!fast) {
+        for (int i = tid; i < n; i += COO_THREADS)
+            if (srow[i] != (i ? srow[i - 1] : prev_row)) atomicOr(&head[i >> 5], 1u << (i & 31));
+        __syncthreads();
+    }
 
-    // ---- one thread per run start; entries are examined lane-contiguously (conflict-free shared reads)
-#pragma unroll 1
-    for (int i = tid; i < n; i += COO_THREADS) {
-        const int r = srow[i];
-        const int before = i ? srow[i - 1] : prev_row;
-        if (r == before) continue;                              // not a run start
-        for (int e = before + 1; e < r; e++) y[e] = 0.0;        // empty rows in front of this run
-        const int stop = min(n, i + COO_LONG + 1);
-        double acc = 0.0;
-        int j = i;
-        for (; j < stop && srow[j] == r; j++) acc = __dadd_rn(acc, prod[j]);
-        if (j == stop && j < n && srow[j] == r) {               // more than COO_LONG entries in this tile
-            long_start[atomicAdd(&n_long, 1)] = i;
-            continue;
+    // ---- one thread per run start among its eight consecutive entries (bits come from one shared word)
+    const int base = tid * COO_IPT;
+    if (base < n) {
+        unsigned mine = (head[base >> 5] >> (base & 31)) & 0xFFu;
+        while (mine) {
+            const int i = base + __ffs(mine) - 1;
+            mine &= mine - 1;
+            // end of the run = next run start (or the end of the tile)
+            int end;
+            {
+                int w = i >> 5;
+                unsigned rest = head[w] & ~((2u << (i & 31)) - 1u);      // bits above i in its word
+                while (!rest && (w + 1) * 32 < n) rest = head[++w];
+                end = rest ? min(n, w * 32 + __ffs(rest) - 1) : n;
+            }
+            const int r = srow[i];
+            const int before = i ? srow[i - 1] : prev_row;
+            for (int e = before + 1; e < r; e++) y[e] = 0.0;    // empty rows in front of this run (beta = 0)
+            if (end - i > COO_LONG) {
+                long_start[atomicAdd(&n_long, 1)] = i;
+                continue;
+            }
+            double acc = 0.0;
+            for (int j = i; j < end; j++) acc = __dadd_rn(acc, prod[j]);
+            y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
         }
-        y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
     }
     if (tid == 0 && n > 0 && srow[0] == prev_row) long_start[atomicAdd(&n_long, 1)] = -1;   // carried-in piece
     if (last_tile && n > 0)
@@ -83,7 +111,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
     __syncthreads();
 
     // ---- one warp per long run / carried-in piece
-    const int lane = tid & 31, warp = tid >> 5;
+    const int warp = tid >> 5;
     for (int q = warp; q < n_long; q += COO_THREADS / 32) {
         const int s = long_start[q];
         const int b = s < 0 ? 0 : s;

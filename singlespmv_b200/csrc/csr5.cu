@@ -213,20 +213,21 @@ c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, c
     // ---- thread-level segmented sums (csr5_spmv_cuda.h:141-176)
     bool direct = starts_row && lane != 0;
     double sum = 0.0, first_sum = 0.0;
-    for (int i0 = 0; i0 < sigma; i0 += 8) {
-        int cc[8];
-        double vv[8], xx[8];
+    constexpr int CH = 4;                       // entries per lane in flight (8: 72 registers, 37 % occupancy in ncu)
+    for (int i0 = 0; i0 < sigma; i0 += CH) {
+        int cc[CH];
+        double vv[CH], xx[CH];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < CH; u++)
             if (i0 + u < sigma) {
                 cc[u] = ld_stream_i1(c + (i0 + u) * C5_OMEGA, pol_stream);
                 vv[u] = ld_stream_d1(v + (i0 + u) * C5_OMEGA, pol_stream);
             }
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < CH; u++)
             if (i0 + u < sigma) xx[u] = ld_x(x + cc[u], pol_x);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < CH; u++) {
             const int i = i0 + u;
             if (i < sigma) {
                 if (i > 0 && ((flags >> (31 - i)) & 1u)) {

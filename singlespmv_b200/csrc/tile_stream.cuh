@@ -17,7 +17,8 @@
 //
 // Variants measured and rejected on B200 (profiles/r1_call8_9_summary.md): scalar lane-contiguous loads (-20 %:
 // 24 instead of 14 load instructions per thread), row_ptr staged in shared memory + warp-local long rows
-// (-15 %: 40 registers -> 6 instead of 8 resident CTAs).  Resident CTAs x 24 KB in flight is what feeds HBM.
+// (-15 %: 40 registers -> 6 instead of 8 resident CTAs), cp.async.bulk.prefetch.L2 of the tile a later wave will
+// stream (-4 % to -27 % with distance).  Resident CTAs x 24 KB in flight is what feeds HBM.
 #pragma once
 #include <map>
 
