@@ -16,6 +16,7 @@
 // is how the schedule arrays are proven to be functionally right, not just equal).
 // CSS runs one tile-stream pass per column block, accumulating into y in block order; with the
 // block's slice of x resident in L2 (that is the point of the format, opt_css.cpp:33-45).
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "tile_stream.cuh"
@@ -307,15 +308,25 @@ struct SsFormat : Format {
 Format *make_ss(const b200spmv_options &o) { return new SsFormat(o); }
 
 // ================================================================= CSS
-__global__ void css_block_key_kernel(const int *__restrict__ col, int nnz, int B, int *__restrict__ key, int *__restrict__ id,
-                                     int *__restrict__ blockNnz)
+constexpr int CSS_HIST = 1024;     // column blocks counted in shared memory (more: global atomics)
+__global__ void css_block_key_kernel(const int *__restrict__ col, int nnz, int B, int nBlock, int *__restrict__ key,
+                                     int *__restrict__ id, int *__restrict__ blockNnz)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    const int b = col[i] / B;                                              // opt_css.cpp:40
-    key[i] = b;
-    id[i] = i;
-    atomicAdd(&blockNnz[b], 1);
+    __shared__ int hist[CSS_HIST];
+    const bool local = nBlock <= CSS_HIST;
+    if (local)
+        for (int k = threadIdx.x; k < nBlock; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x) {
+        const int b = col[i] / B;                                          // opt_css.cpp:40
+        key[i] = b;
+        id[i] = i;
+        atomicAdd(local ? &hist[b] : &blockNnz[b], 1);
+    }
+    __syncthreads();
+    if (local)
+        for (int k = threadIdx.x; k < nBlock; k += blockDim.x)
+            if (hist[k]) atomicAdd(&blockNnz[k], hist[k]);
 }
 // entry k of the block-sorted order goes to slab position base[b] + (k - start[b])
 __global__ void css_scatter_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
@@ -369,7 +380,7 @@ struct CssFormat : Format {
         B2_TRY(slabBase.alloc((size_t)nBlock + 1));
         B2_CUDA(cudaMemsetAsync(blockNnz.p, 0, blockNnz.bytes(), s));
         if (nnz) {
-            css_block_key_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(A.col, nnz, B, key.p, id.p, blockNnz.p);
+            css_block_key_kernel<<<std::min(ceil_div(nnz, 256), 148 * 16), 256, 0, s>>>(A.col, nnz, B, nBlock, key.p, id.p, blockNnz.p);
             B2_KERNEL_CHECK();
             int bits = 1;
             while ((1 << bits) < nBlock) bits++;
