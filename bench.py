@@ -377,9 +377,11 @@ def main():
     ap.add_argument("--segment-width", type=int, default=0)
     ap.add_argument("--n-block", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=0)
+    ap.add_argument("--value-f32", action="store_true", help="CRS: fp32 storage of the matrix values, fp64 arithmetic")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    args.options = dict(segment_width=args.segment_width, n_block=args.n_block, csr5_sigma=args.sigma)
+    args.options = dict(segment_width=args.segment_width, n_block=args.n_block, csr5_sigma=args.sigma,
+                        value_f32=1 if args.value_f32 else 0)
     wl_key = args.workload or ("c2" if args.gpus == 1 else "c5")
     wl = dict(WORKLOADS[wl_key])
     if args.mini:

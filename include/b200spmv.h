@@ -68,7 +68,9 @@ typedef struct {
     int csr5_sigma;      /* CSR5: sigma; 0 = auto (anonymouslib_cuda.h:293-317) */
     int ss_faithful;     /* SS/CSS: 1 = three-phase Mul/fold/gather with val_buf, the reference's
                             operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
-    int reserved[12];
+    int value_f32;       /* CRS: 1 = store the matrix values as fp32 (rounded once at conversion); x, y and all
+                            arithmetic stay fp64.  8 instead of 12 B/nnz; tolerance 1e-5 (BASELINE.json north star) */
+    int reserved[11];
 } b200spmv_options;
 
 /* ---- library ---- */

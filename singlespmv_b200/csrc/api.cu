@@ -111,6 +111,10 @@ int b200spmv_create(int format, const b200spmv_options *opts, b200spmv_matrix **
         set_error("create: bad option (n_block=%d csr5_sigma=%d)", o.n_block, o.csr5_sigma);
         return B200SPMV_ERR_INVALID;
     }
+    if (o.value_f32 && format != B200SPMV_CRS) {
+        set_error("create: value_f32 is implemented for the CRS format only");
+        return B200SPMV_ERR_UNSUPPORTED;
+    }
     Format *f = make_format(format, o);
     if (!f) {
         set_error("create: unknown format %d", format);

@@ -245,7 +245,7 @@ struct SsFormat : Format {
             B2_KERNEL_CHECK();
         }
         B2_TRY(build_chain(row2d.p, H, W, seg_index.p, &nStep, counts, segs, s));
-        B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, nRow, nnz, s));
+        B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, s));
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
@@ -427,7 +427,7 @@ struct CssFormat : Format {
             int *rp = row_ptr.p + (size_t)b * ((size_t)nRow + 1);
             B2_TRY(build_row_ptr(row2d.p + k.base, k.cnt, nRow, rp, s));
             B2_TRY(build_chain(row2d.p + k.base, k.H, W, seg_index.p + seg0, &k.nStep, k.counts, k.segs, s));
-            B2_TRY(k.ts.build(rp, col2d.p + k.base, val2d.p + k.base, nRow, k.cnt, s));
+            B2_TRY(k.ts.build(rp, col2d.p + k.base, val2d.p + k.base, false, nRow, k.cnt, s));
             seg0 += k.H;
         }
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));

@@ -26,9 +26,31 @@ __global__ void tile_row_kernel(const int *__restrict__ ptr, int nRow, int nTile
     tile_row[t] = lo;
 }
 
+// four consecutive matrix values as doubles: fp64 storage = two 128-bit loads, fp32 storage = one
+__device__ __forceinline__ void ld_val4(const double *p, uint64_t pol, double &a, double &b, double &c, double &d)
+{
+    const double2 lo = ld_stream_d2(p, pol), hi = ld_stream_d2(p + 2, pol);
+    a = lo.x; b = lo.y; c = hi.x; d = hi.y;
+}
+__device__ __forceinline__ void ld_val4(const float *p, uint64_t pol, double &a, double &b, double &c, double &d)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    a = r.x; b = r.y; c = r.z; d = r.w;                 // fp32 -> fp64 is exact
+}
+__device__ __forceinline__ double ld_val1(const double *p, uint64_t pol) { return ld_stream_d1(p, pol); }
+__device__ __forceinline__ double ld_val1(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return (double)r;
+}
+
+template <typename VT>
 __global__ void __launch_bounds__(TS_THREADS)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
-                   const double *__restrict__ val, const int *__restrict__ tile_row,
+                   const VT *__restrict__ val, const int *__restrict__ tile_row,
                    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
                    int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok)
 {
@@ -52,8 +74,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         for (int k = 0; k < TS_IPT / 4; k++) {
             const int e = t0 + 4 * (tid + k * TS_THREADS);
             c[k] = ld_stream_i4(col + e, pol_stream);
-            v[2 * k] = ld_stream_d2(val + e, pol_stream);
-            v[2 * k + 1] = ld_stream_d2(val + e + 2, pol_stream);
+            ld_val4(val + e, pol_stream, v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
         }
         double xs[TS_IPT];
 #pragma unroll
@@ -72,7 +93,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         }
     } else {
         for (int i = tid; i < t1 - t0; i += TS_THREADS)
-            prod[i] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream),
+            prod[i] = __dmul_rn(ld_val1(val + t0 + i, pol_stream),
                                 ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
     }
 
@@ -127,8 +148,9 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
 
 // Finishes the rows that cross tile boundaries; one thread per tile, only the FIRST carrying
 // tile of a row acts.  Short rows are recomputed from global memory in the reference's order.
+template <typename VT>
 __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
-                                  const double *__restrict__ val, const int *__restrict__ tile_row,
+                                  const VT *__restrict__ val, const int *__restrict__ tile_row,
                                   const double *__restrict__ x, double *__restrict__ y,
                                   const double *__restrict__ carry, int tileLo, int tileHi, int rowLo,
                                   int rowHi, int accumulate)
@@ -145,7 +167,7 @@ __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__
     if (t != b / TS_TILE + 1) return;
     if (e - b <= TS_LONG) {
         double acc = 0.0;
-        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn(val[j], x[col[j]]));
+        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn((double)val[j], x[col[j]]));
         y[rc] = accumulate ? __dadd_rn(y[rc], acc) : acc;
     } else {
         const int last = (e - 1) / TS_TILE;
@@ -155,9 +177,10 @@ __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__
     }
 }
 
-int TileStream::build(const int *row_ptr_d, const int *col_d, const double *val_d, int nRow_, int nnz_,
+int TileStream::build(const int *row_ptr_d, const int *col_d, const void *val_d, bool val_is_f32, int nRow_, int nnz_,
                       cudaStream_t s)
 {
+    f32 = val_is_f32;
     row_ptr = row_ptr_d;
     col = col_d;
     val = val_d;
@@ -203,16 +226,18 @@ int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int 
         return B200SPMV_OK;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
-    tile_stream_kernel<<<tileHi - tileLo, TS_THREADS, 0, s>>>(row_ptr, col, val, tile_row.p, x, y, carry.p,
-                                                             nnz, tileLo, rowLo, rowHi, accumulate ? 1 : 0,
-                                                             vec_ok);
-    B2_KERNEL_CHECK();
-    if (tileHi - tileLo > 1 || tileLo > 0) {
-        tile_fixup_kernel<<<ceil_div(tileHi - tileLo, 256), 256, 0, s>>>(row_ptr, col, val, tile_row.p, x, y,
-                                                                        carry.p, tileLo, tileHi, rowLo, rowHi,
-                                                                        accumulate ? 1 : 0);
-        B2_KERNEL_CHECK();
+    const int nT = tileHi - tileLo, acc = accumulate ? 1 : 0;
+    const bool fix = nT > 1 || tileLo > 0;
+    if (f32) {
+        const float *v = static_cast<const float *>(val);
+        tile_stream_kernel<float><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
+        if (fix) tile_fixup_kernel<float><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
+    } else {
+        const double *v = static_cast<const double *>(val);
+        tile_stream_kernel<double><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
+        if (fix) tile_fixup_kernel<double><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
     }
+    B2_KERNEL_CHECK();
     return B200SPMV_OK;
 }
 

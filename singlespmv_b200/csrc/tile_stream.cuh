@@ -36,14 +36,15 @@ struct TileStream {
     // borrowed
     const int *row_ptr = nullptr;   // [nRow+1]
     const int *col = nullptr;       // [nnz] (may be padded beyond nnz; padding is never read)
-    const double *val = nullptr;
+    const void *val = nullptr;      // double[nnz], or float[nnz] when f32 (fp32 storage, fp64 arithmetic)
+    bool f32 = false;
     int nRow = 0, nnz = 0;
     // owned
     int nTiles = 0;
     DevBuf<int> tile_row;           // [nTiles+1]: first row whose first entry is >= tile start
     DevBuf<double> carry;           // [nTiles]
 
-    int build(const int *row_ptr_d, const int *col_d, const double *val_d, int nRow_, int nnz_,
+    int build(const int *row_ptr_d, const int *col_d, const void *val_d, bool val_is_f32, int nRow_, int nnz_,
               cudaStream_t s);
     // y[rowLo..rowHi) = (accumulate ? y : 0) + A x, restricted to tiles [tileLo, tileHi)
     int run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo, int tileHi,

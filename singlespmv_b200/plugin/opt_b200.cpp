@@ -49,6 +49,9 @@ void OptimizeProblem (const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_o
     opt.segment_width = SEGMENT_WIDTH;
     opt.n_block = N_BLOCK;
     opt.csr5_sigma = B200_SIGMA;
+#ifdef B200_VALUE_F32
+    opt.value_f32 = 1;              // CRS only: fp32 storage of the matrix values, fp64 arithmetic
+#endif
     b200_check(b200spmv_create(B200_FORMAT_ENUM, &opt, &A_opt.handle), "create");
     b200_check(b200spmv_convert_coo_host(A_opt.handle, A.nRow, A.nCol, A.nNnz, A.row_idx, A.col_idx, A.val), "convert");
 #ifdef B200_DEVICE_RESIDENT

@@ -148,6 +148,25 @@ def test_host_multiply_pipeline_large(sp, oracle, fmt, opt):
         assert np.array_equal(y, y_ref)
 
 
+def test_crs_f32_storage(sp, oracle, all_cases):
+    """options.value_f32: values rounded to fp32 once, arithmetic in fp64.  Two checks: (1) bit-identical to the
+    fp64 path run on the rounded matrix (fp32 -> fp64 widening is exact), (2) within the north star's 1e-5 of the
+    reference CRS result on the unrounded matrix."""
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        val32 = val.astype(np.float32).astype(np.float64)
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        A_opt, y = run_host(sp, "crs", nRow, nCol, row, col, val, x, value_f32=1)
+        assert A_opt.scalar("value_f32") == 1
+        assert A_opt.scalar("alg_bytes") == 8 * len(row) + 4 * (nRow + 1) + 8 * nCol + 8 * nRow
+        assert np.array_equal(A_opt.array("val", np.float64), val32), name
+        _, y64 = run_host(sp, "crs", nRow, nCol, row, col, val32, x)
+        assert np.array_equal(y, y64), name
+        assert_y(y, y_ref, row, col, val, x, nRow, tol=1e-5)
+    with pytest.raises(sp.B200SpmvError) as e:
+        sp.SpMatOpt("ell", value_f32=1)
+    assert e.value.status == -3
+
+
 # ------------------------------------------------------------------------------------------ ELL
 def test_ell(sp, oracle, all_cases):
     for name, nRow, nCol, row, col, val, x in all_cases:
