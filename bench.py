@@ -51,6 +51,17 @@ MINI = {"c1": dict(p0=128), "c2": dict(p0=1 << 16), "c3": dict(p0=14, p1=1 << 18
         "c5": dict(p0=64)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
+# captures (profiles/r1_ncu_kernels.md).  Keyed by (workload, format, n_block); anything else reports null.
+NCU_TRAFFIC = {("c2", "css", 3): 2415011680, ("c2", "ell", 0): 37576549544, ("c2", "jds", 0): 33652983616,
+               ("c3", "crs", 0): 3308867896, ("c3", "csr5", 0): 3383375304, ("c4", "dia", 0): 3864375128,
+               ("c4", "ell", 0): 5853024560, ("c5", "crs", 0): 13933793000, ("c5", "coo", 0): 17818634000,
+               ("c1", "crs", 0): 77940224}
+DOMINANT = {"crs": "tile_stream_kernel", "ss": "tile_stream_kernel", "css": "tile_stream_kernel (one launch per column block)",
+            "ell": "ell_spmv_kernel", "jds": "jds_spmv_kernel", "dia": "dia_spmv_tma_kernel", "coo": "coo_tile_kernel",
+            "csr5": "c5_compute_kernel"}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -218,6 +229,11 @@ def run_single(args, wl, wl_key):
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     options = dict(args.options)
+    if fmt == "auto":                        # the engine's own pick from the matrix statistics (b200spmv_recommend_format)
+        fmt, rec_opts = coo.recommend()
+        for k, v in rec_opts.items():
+            if not options.get(k):
+                options[k] = v
     if not args.format:                      # the workload's own tunables apply to its default format only
         for k, v in wl.get("opts", {}).items():
             if not options.get(k):
@@ -270,6 +286,16 @@ def run_single(args, wl, wl_key):
         b.record(stream)
         torch.cuda.synchronize()
         total_ms = a.elapsed_time(b)
+    warm_ms = None
+    if need_flush:
+        # for matrices that fit in L2 report the warm (L2-hot, back-to-back) figure as well
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        warm_ms = a.elapsed_time(b) / args.steps
     # keep the sampler running over the e2e loop as well
     ms = total_ms / args.steps
     gflops = 2.0 * nnz / (ms * 1e-3) / 1e9
@@ -287,16 +313,24 @@ def run_single(args, wl, wl_key):
 
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
+    # the dominant kernel runs once per step, except CSS: once per column block (each streaming 1/nBlock of the matrix)
+    dom_launches = A.scalar("nBlock") if fmt == "css" else 1
+    traffic = None if args.mini else NCU_TRAFFIC.get((wl_key, fmt, options.get("n_block", 0) if fmt == "css" else 0))
     line = {"metric": "SpMV GFLOP/s", "value": gflops, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "options": {k: v for k, v in options.items() if v}, "nRow": nRow, "nCol": nCol, "nnz": nnz,
                        "x": "srand(3) rand()/RAND_MAX (src/main.cpp:18,31)",
                        "l2": "flushed between steps (512 MiB write)" if need_flush else "inputs larger than L2 (%.2f GB streamed per step)" % (alg_bytes / 1e9),
-                       "convert_ms": t_conv * 1e3, "generate_ms": t_gen * 1e3},
+                       "convert_ms": t_conv * 1e3, "generate_ms": t_gen * 1e3,
+                       **({"warm_l2_ms_per_step": warm_ms, "warm_l2_gflops": 2.0 * nnz / (warm_ms * 1e-3) / 1e9} if warm_ms else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
-                         "kernel": A.kernel_name() if hasattr(A, "kernel_name") else fmt},
+                         "traffic": traffic, "peak_source": peak_src, "kernel": DOMINANT.get(fmt, fmt),
+                         "alg_bytes_per_launch": alg_bytes // dom_launches, "dominant_launches_per_step": dom_launches,
+                         "avg_launch_ms": ms / dom_launches,
+                         "note": "achieved = alg_bytes_per_launch / avg_launch_ms (CUDA events over the timed region; the "
+                                 "fix-up kernel's ~5 % share is inside); traffic = ncu dram read+write of one launch, "
+                                 "profiles/r1_ncu_kernels.md"},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": 8 * nCol, "d2h_bytes_per_step": 8 * nRow},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks}

@@ -175,6 +175,32 @@ B200SPMV_API int b200spmv_halo_set_send(b200spmv_halo *h, const int *send_cols_h
 B200SPMV_API int b200spmv_halo_pack(const b200spmv_halo *h, const double *x_owned_d, double *sendbuf_d, void *stream);
 B200SPMV_API int b200spmv_halo_free(b200spmv_halo *h);
 
+/* ---- Matrix-Market ingest into a device COO.  The reference's loader (src/util.cpp:30-66)
+ * ignores the banner and keeps duplicates; the CSR5 benchmark it vendors reads the same files through mmio and
+ * honours symmetric / pattern banners (opt/Benchmark_SpMV_using_CSR5/CSR5_avx2/main.cpp:145-282). */
+typedef enum {
+    B200SPMV_MTX_BANNER    = 0,  /* real|integer|pattern x general|symmetric|skew-symmetric; mirrored entries added,
+                                    duplicate coordinates summed: the result satisfies the plugins' input contract */
+    B200SPMV_MTX_REFERENCE = 1   /* src/util.cpp:30-66 bit for bit: banner ignored, exactly L triples, duplicates kept */
+} b200spmv_mtx_mode;
+/* Parses on the host, sorts by (row, col) (and reduces duplicates) on the device.  Free with b200spmv_coo_free. */
+B200SPMV_API int b200spmv_load_mtx(const char *path, int mode, b200spmv_coo *out, void *stream);
+
+/* ---- matrix statistics and format recommendation.  The statistics are those the reference's
+ * tooling prints (matrix/script/counter.cpp:19-42: max/min non-zeros per row and per column, variance of the
+ * row counts) plus empty rows and the number of non-empty diagonals (src/opt_dia.cpp:29-34). */
+typedef struct {
+    int nRow, nCol;
+    long long nnz;
+    int rowMax, rowMin, colMax, colMin;
+    double rowMean, rowVar;          /* rowVar = sum (cnt - mean)^2 / nRow, as counter.cpp:31-34 */
+    long long nEmptyRows, nDiag;
+} b200spmv_stats;
+B200SPMV_API int b200spmv_analyze(const b200spmv_coo *coo /* whole matrix */, b200spmv_stats *out, void *stream);
+/* Returns a b200spmv_format; opts_out (may be NULL) receives the tunables that go with it (CSS: n_block).
+ * Rules and the measurements behind them: singlespmv_b200/csrc/analyze.cu, profiles/. */
+B200SPMV_API int b200spmv_recommend_format(const b200spmv_stats *stats, b200spmv_options *opts_out);
+
 /* x = rand()/RAND_MAX stream of src/util.cpp:92-102 after srand(seed) (src/main.cpp:18):
  * writes x_h[0..nCol) (and y_h[0..nRow) if y_h != NULL), host side, glibc rand(). */
 B200SPMV_API int b200spmv_reference_vectors(unsigned seed, int nCol, int nRow, double *x_h, double *y_h);

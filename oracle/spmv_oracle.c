@@ -453,3 +453,33 @@ ORC_API void orc_reference_vectors(unsigned seed, int nCol, int nRow, double *x,
     for (int i = 0; i < nCol; i++) x[i] = (double)rand() / RAND_MAX;
     for (int i = 0; i < nRow; i++) { double v = (double)rand() / RAND_MAX; if (y) y[i] = v; }
 }
+
+/* ------------------------------------------------------------ statistics ---- */
+
+/* matrix/script/counter.cpp:19-42 -- non-zeros per row and per column: max/min of each, and the variance of
+ * the row counts, accumulated term by term like the reference does.  out5 = rowMax,rowMin,colMax,colMin,nDiag'
+ * where nDiag' (not in counter.cpp) is the number of distinct col-row values (src/opt_dia.cpp:29-34). */
+ORC_API double orc_counter(int nRow, int nCol, int nnz, const int *row, const int *col, long long *out5)
+{
+    int *cr = (int *)calloc((size_t)(nRow > 0 ? nRow : 1), sizeof(int));
+    int *cc = (int *)calloc((size_t)(nCol > 0 ? nCol : 1), sizeof(int));
+    size_t N = (size_t)nRow + (size_t)nCol;
+    unsigned char *seen = (unsigned char *)calloc(N ? N : 1, 1);
+    for (int i = 0; i < nnz; i++) { cr[row[i]]++; cc[col[i]]++; seen[col[i] - row[i] + (nRow - 1)] = 1; }
+    int rmax = 0, rmin = nRow ? cr[0] : 0, cmax = 0, cmin = nCol ? cc[0] : 0;
+    double ave = nRow ? (double)nnz / nRow : 0, var = 0;
+    for (int r = 0; r < nRow; r++) {
+        if (cr[r] > rmax) rmax = cr[r];
+        if (cr[r] < rmin) rmin = cr[r];
+        var += (cr[r] - ave) * (cr[r] - ave) / nRow;
+    }
+    for (int c = 0; c < nCol; c++) {
+        if (cc[c] > cmax) cmax = cc[c];
+        if (cc[c] < cmin) cmin = cc[c];
+    }
+    long long nd = 0;
+    for (size_t d = 0; d < N; d++) nd += seen[d];
+    out5[0] = rmax; out5[1] = rmin; out5[2] = cmax; out5[3] = cmin; out5[4] = nd;
+    free(cr); free(cc); free(seen);
+    return var;
+}

@@ -24,6 +24,12 @@ class Options(C.Structure):
                 ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("reserved", C.c_int * 11)]
 
 
+class Stats(C.Structure):
+    _fields_ = [("nRow", C.c_int), ("nCol", C.c_int), ("nnz", C.c_longlong), ("rowMax", C.c_int), ("rowMin", C.c_int),
+                ("colMax", C.c_int), ("colMin", C.c_int), ("rowMean", C.c_double), ("rowVar", C.c_double),
+                ("nEmptyRows", C.c_longlong), ("nDiag", C.c_longlong)]
+
+
 class Coo(C.Structure):
     _fields_ = [("nRow", C.c_int), ("nCol", C.c_int), ("rowBegin", C.c_int), ("rowEnd", C.c_int),
                 ("nnz", C.c_longlong), ("row_d", C.c_void_p), ("col_d", C.c_void_p),
@@ -55,6 +61,9 @@ def _load():
     lib.b200spmv_coo_free.argtypes = [C.POINTER(Coo)]
     lib.b200spmv_coo_download.argtypes = [C.POINTER(Coo), vp, vp, vp]
     lib.b200spmv_reference_vectors.argtypes = [C.c_uint, ip, ip, vp, vp]
+    lib.b200spmv_load_mtx.argtypes = [C.c_char_p, ip, C.POINTER(Coo), vp]
+    lib.b200spmv_analyze.argtypes = [C.POINTER(Coo), C.POINTER(Stats), vp]
+    lib.b200spmv_recommend_format.argtypes = [C.POINTER(Stats), C.POINTER(Options)]
     lib.b200spmv_partition_rows.argtypes = [vp, ll, ip, ip, vp]
     lib.b200spmv_partition_synth.argtypes = [ip, ll, ll, ip, vp]
     lib.b200spmv_halo_plan.argtypes = [C.POINTER(Coo), ip, ip, C.POINTER(vp), vp]

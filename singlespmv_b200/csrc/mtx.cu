@@ -1,0 +1,159 @@
+// mtx.cu -- Matrix-Market ingest straight into a device COO.
+// The reference's loader (/root/reference/src/util.cpp:30-66) skips '%' lines, reads "M N L" and then exactly L
+// "row col val" triples (1-based), sorts by (row, col), keeps duplicates and IGNORES the banner, so symmetric and
+// pattern files are mis-read.  The CSR5 benchmark it vendors reads the same files through
+// NIST's mmio and does honour the banner (opt/Benchmark_SpMV_using_CSR5/CSR5_avx2/main.cpp:145-282).  Both
+// behaviours are offered:
+//   B200SPMV_MTX_BANNER    (default) real/integer/pattern x general/symmetric/skew-symmetric, mirrored entries
+//                          added, duplicate coordinates summed -> satisfies the plugins' input contract
+//   B200SPMV_MTX_REFERENCE the reference loader's semantics, bit for bit (duplicates kept, banner ignored)
+// Parsing is host work (text); sorting, mirroring bookkeeping and duplicate reduction run on the device.
+#include <cub/cub.cuh>
+
+#include <cerrno>
+#include <cstdlib>
+#include <string>
+
+#include "common.cuh"
+
+using namespace b2;
+
+namespace {
+
+__global__ void mtx_unpack_kernel(const unsigned long long *__restrict__ key, long long n, int *__restrict__ row, int *__restrict__ col)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    row[i] = (int)(key[i] >> 32);
+    col[i] = (int)(key[i] & 0xFFFFFFFFull);
+}
+
+struct Parsed {
+    int M = 0, N = 0;
+    std::vector<unsigned long long> key;
+    std::vector<double> val;
+};
+
+static bool starts_with(const char *s, const char *p) { return strncmp(s, p, strlen(p)) == 0; }
+
+static int parse_file(const char *path, int mode, Parsed &out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("load_mtx: cannot open '%s': %s", path, strerror(errno)); return B200SPMV_ERR_INVALID; }
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::string buf((size_t)(size > 0 ? size : 0), '\0');
+    if (size > 0 && fread(&buf[0], 1, (size_t)size, f) != (size_t)size) { fclose(f); set_error("load_mtx: short read on '%s'", path); return B200SPMV_ERR_INVALID; }
+    fclose(f);
+    const char *p = buf.c_str(), *end = p + buf.size();
+    bool pattern = false, symmetric = false, skew = false;
+    bool first = true;
+    // comment / banner lines
+    while (p < end && *p == '%') {
+        const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        if (first && mode == B200SPMV_MTX_BANNER && starts_with(p, "%%MatrixMarket")) {
+            std::string line(p, eol);
+            for (auto &ch : line) ch = (char)tolower((unsigned char)ch);
+            if (line.find("coordinate") == std::string::npos) { set_error("load_mtx: only 'coordinate' files are supported (%s)", line.c_str()); return B200SPMV_ERR_UNSUPPORTED; }
+            if (line.find("complex") != std::string::npos || line.find("hermitian") != std::string::npos) { set_error("load_mtx: complex matrices are not supported"); return B200SPMV_ERR_UNSUPPORTED; }
+            pattern = line.find("pattern") != std::string::npos;
+            skew = line.find("skew-symmetric") != std::string::npos;
+            symmetric = !skew && line.find("symmetric") != std::string::npos;
+        }
+        first = false;
+        p = eol < end ? eol + 1 : end;
+    }
+    char *q = nullptr;
+    const long M = strtol(p, &q, 10); p = q;
+    const long N = strtol(p, &q, 10); p = q;
+    const long L = strtol(p, &q, 10); p = q;
+    if (M < 0 || N < 0 || L < 0 || M > 0x7fffffffL || N > 0x7fffffffL) { set_error("load_mtx: bad size line in '%s'", path); return B200SPMV_ERR_INVALID; }
+    out.M = (int)M; out.N = (int)N;
+    out.key.reserve((size_t)L * ((symmetric || skew) ? 2 : 1));
+    out.val.reserve(out.key.capacity());
+    for (long i = 0; i < L; i++) {
+        const long r = strtol(p, &q, 10);
+        if (q == p) { set_error("load_mtx: '%s' ends after %ld of %ld entries", path, i, L); return B200SPMV_ERR_INVALID; }
+        p = q;
+        const long c = strtol(p, &q, 10); p = q;
+        double v = 1.0;
+        if (!pattern) { v = strtod(p, &q); p = q; }
+        if (r < 1 || c < 1 || r > M || c > N) { set_error("load_mtx: entry %ld (%ld,%ld) outside the %ldx%ld matrix", i, r, c, M, N); return B200SPMV_ERR_INVALID; }
+        out.key.push_back(((unsigned long long)(r - 1) << 32) | (unsigned long long)(c - 1));
+        out.val.push_back(v);
+        if ((symmetric || skew) && r != c) {
+            if (c > M || r > N) { set_error("load_mtx: symmetric file is not square"); return B200SPMV_ERR_INVALID; }
+            out.key.push_back(((unsigned long long)(c - 1) << 32) | (unsigned long long)(r - 1));
+            out.val.push_back(skew ? -v : v);
+        }
+    }
+    return B200SPMV_OK;
+}
+
+}  // namespace
+
+extern "C" int b200spmv_load_mtx(const char *path, int mode, b200spmv_coo *out, void *stream)
+{
+    clear_error();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!path || !out) { set_error("load_mtx: NULL argument"); return B200SPMV_ERR_INVALID; }
+    if (mode != B200SPMV_MTX_BANNER && mode != B200SPMV_MTX_REFERENCE) { set_error("load_mtx: unknown mode %d", mode); return B200SPMV_ERR_INVALID; }
+    memset(out, 0, sizeof *out);
+    Parsed P;
+    B2_TRY(parse_file(path, mode, P));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("load_mtx: no CUDA device available; libb200spmv has no CPU fallback");
+        return B200SPMV_ERR_CUDA;
+    }
+    const long long n = (long long)P.key.size();
+    if (n > 0x7fffffffLL) { set_error("load_mtx: %lld entries exceed int32", n); return B200SPMV_ERR_INVALID; }
+    out->nRow = P.M; out->nCol = P.N; out->rowBegin = 0; out->rowEnd = P.M;
+    DevBuf<unsigned long long> k0, k1;
+    DevBuf<double> v0, v1;
+    DevBuf<long long> nout;
+    B2_TRY(k0.alloc((size_t)n)); B2_TRY(k1.alloc((size_t)n));
+    B2_TRY(v0.alloc((size_t)n)); B2_TRY(v1.alloc((size_t)n));
+    B2_TRY(nout.alloc(1));
+    long long nnz = n;
+    const unsigned long long *keys = k1.p;
+    const double *vals = v1.p;
+    if (n) {
+        B2_CUDA(cudaMemcpyAsync(k0.p, P.key.data(), sizeof(unsigned long long) * (size_t)n, cudaMemcpyHostToDevice, s));
+        B2_CUDA(cudaMemcpyAsync(v0.p, P.val.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        size_t tmp = 0;      // stable: entries with equal coordinates keep their file order (= std::sort's input order is NOT
+                             // guaranteed by the reference; with duplicates its order is implementation-defined)
+        B2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0.p, k1.p, v0.p, v1.p, (int)n, 0, 64, s));
+        {
+            DevBuf<char> t;
+            B2_TRY(t.alloc(tmp));
+            B2_CUDA(cub::DeviceRadixSort::SortPairs(t.p, tmp, k0.p, k1.p, v0.p, v1.p, (int)n, 0, 64, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+        }
+        if (mode == B200SPMV_MTX_BANNER) {              // duplicate coordinates are summed (in file order)
+            B2_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp, k1.p, k0.p, v1.p, v0.p, nout.p, cub::Sum(), (int)n, s));
+            DevBuf<char> t;
+            B2_TRY(t.alloc(tmp));
+            B2_CUDA(cub::DeviceReduce::ReduceByKey(t.p, tmp, k1.p, k0.p, v1.p, v0.p, nout.p, cub::Sum(), (int)n, s));
+            B2_CUDA(cudaMemcpyAsync(&nnz, nout.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+            keys = k0.p;
+            vals = v0.p;
+        }
+    }
+    const size_t cnt = nnz > 0 ? (size_t)nnz : 1;
+    B2_CUDA(cudaMalloc((void **)&out->row_d, cnt * sizeof(int)));
+    B2_CUDA(cudaMalloc((void **)&out->col_d, cnt * sizeof(int)));
+    B2_CUDA(cudaMalloc((void **)&out->val_d, cnt * sizeof(double)));
+    out->nnz = nnz;
+    if (nnz) {
+        mtx_unpack_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(keys, nnz, out->row_d, out->col_d);
+        B2_KERNEL_CHECK();
+        B2_CUDA(cudaMemcpyAsync(out->val_d, vals, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+    }
+    B2_CUDA(cudaStreamSynchronize(s));
+    return B200SPMV_OK;
+}

@@ -320,6 +320,27 @@ def run_partitioned_bench(args, wl, wl_key):
     ms = float(t.item()) / args.steps
     dist.barrier()
 
+    # exposed communication: eager full step vs the same launches without the exchange
+    def compute_only():
+        cptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        b.multiply_interior(cptr)
+        b.multiply_boundary(cptr)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        dist.barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(eng.compute)
+        for _ in range(args.steps):
+            fn()
+        eb.record(eng.compute)
+        torch.cuda.synchronize()
+        tt = torch.tensor([ea.elapsed_time(eb) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+    eager_full_ms = timed(eng._step_eager)
+    compute_only_ms = timed(compute_only)
+
     # e2e: per step H2D of the owned x slice, exchange + multiply, D2H of the owned y slice
     def e2e_step():
         b.x_owned.copy_(x_pin, non_blocking=True)
@@ -352,6 +373,8 @@ def run_partitioned_bench(args, wl, wl_key):
                            "parallelism": "row blocks by nnz balance x%d, x halo %d doubles/step over NCCL send/recv "
                                           "overlapped with interior rows" % (world, halo_total),
                            "launch": "one CUDA graph per step (both streams + NCCL captured)" if graphed else "eager launches",
+                           "eager_ms_per_step": eager_full_ms, "compute_only_ms_per_step": compute_only_ms,
+                           "exposed_exchange_ms": max(0.0, eager_full_ms - compute_only_ms),
                            "l2": "inputs larger than L2 (%.2f GB per GPU per step)" % (alg_bytes / world / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None,

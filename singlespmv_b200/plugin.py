@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FORMATS, SYNTH, B200SpmvError, Coo, Options, check, lib
+from ._lib import FORMATS, SYNTH, B200SpmvError, Coo, Options, Stats, check, lib
 
 
 def _ptr(a):
@@ -45,16 +45,42 @@ class DeviceCoo:
 
     def __init__(self, kind, p0, p1=0, seed=1, row_begin=0, row_end=0, stream=None):
         self.c = Coo()
-        check(lib.b200spmv_synth(SYNTH[kind], int(p0), int(p1), int(seed), int(row_begin), int(row_end),
-                                 C.byref(self.c), stream))
+        if kind is not None:
+            check(lib.b200spmv_synth(SYNTH[kind], int(p0), int(p1), int(seed), int(row_begin), int(row_end),
+                                     C.byref(self.c), stream))
+            self._dims()
+
+    def _dims(self):
         self.nRow, self.nCol, self.nNnz = self.c.nRow, self.c.nCol, int(self.c.nnz)
         self.rowBegin, self.rowEnd = self.c.rowBegin, self.c.rowEnd
+
+    @classmethod
+    def from_mtx(cls, path, reference_semantics=False, stream=None):
+        """Matrix-Market file -> device COO (b200spmv_load_mtx).  reference_semantics: src/util.cpp:30-66 exactly."""
+        self = cls(None, 0)
+        check(lib.b200spmv_load_mtx(str(path).encode(), 1 if reference_semantics else 0, C.byref(self.c), stream))
+        self._dims()
+        return self
 
     def to_host(self):
         n = self.nNnz
         row, col, val = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
         check(lib.b200spmv_coo_download(C.byref(self.c), _ptr(row), _ptr(col), _ptr(val)))
         return self.nRow, self.nCol, row, col, val
+
+    def analyze(self):
+        """Row/column statistics (reference matrix/script/counter.cpp) + diagonals, computed on the device."""
+        st = Stats()
+        check(lib.b200spmv_analyze(C.byref(self.c), C.byref(st), None))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}, st
+
+    def recommend(self):
+        """(format name, options dict) the engine would pick for this matrix."""
+        _, st = self.analyze()
+        o = Options()
+        f = check(lib.b200spmv_recommend_format(C.byref(st), C.byref(o)))
+        name = [k for k, v in FORMATS.items() if v == f][0]
+        return name, {k: getattr(o, k) for k in ("segment_width", "n_block", "csr5_sigma") if getattr(o, k)}
 
     def free(self):
         if self.c is not None:

@@ -275,6 +275,15 @@ class Oracle:
                                m["val"].ctypes, x.ctypes, y.ctypes)
         return y
 
+    # ---- statistics (reference matrix/script/counter.cpp)
+    def counter(self, nRow, nCol, row, col):
+        row, col = _i32(row), _i32(col)
+        out = np.zeros(5, np.int64)
+        self.lib.orc_counter.restype = C.c_double
+        var = self.lib.orc_counter(C.c_int(nRow), C.c_int(nCol), C.c_int(len(row)), row.ctypes, col.ctypes, out.ctypes)
+        return {"rowMax": int(out[0]), "rowMin": int(out[1]), "colMax": int(out[2]), "colMin": int(out[3]),
+                "nDiag": int(out[4]), "rowVar": float(var)}
+
     # ---- reference verifier and vectors (src/util.cpp:67-102, src/main.cpp:18,31-32)
     def verify(self, nRow, row, col, val, x, y):
         row, col, val, x, y = _i32(row), _i32(col), _f64(val), _f64(x), _f64(y)

@@ -558,3 +558,38 @@ def test_partition_rows_from_coo(sp, oracle):
         assert b[0] == 0 and b[-1] == d.nRow and np.all(np.diff(b) >= 0)
         per = np.diff(ptr[b])
         assert per.max() - per.min() <= 2 * np.diff(ptr).max()        # balanced up to one row
+
+
+# ------------------------------------------------------------------------------------------ statistics + recommendation
+@pytest.mark.parametrize("kind,p0,p1,expect", [("lap2d5", 300, 0, "dia"), ("box3d27", 40, 0, "dia"), ("lap3d7", 50, 0, "dia"),
+                                                ("uniform", 1 << 16, 32, "ell"), ("rmat", 15, 1 << 20, "csr5")])
+def test_analyze_and_recommend(sp, oracle, kind, p0, p1, expect):
+    d = sp.DeviceCoo(kind, p0, p1, 42 if kind == "rmat" else 1)
+    nRow, nCol, row, col, val = d.to_host()
+    st, _ = d.analyze()
+    ref = oracle.counter(nRow, nCol, row, col)            # matrix/script/counter.cpp restated
+    for k in ("rowMax", "rowMin", "colMax", "colMin", "nDiag"):
+        assert st[k] == ref[k], k
+    assert st["nnz"] == len(row) and st["nEmptyRows"] == int((np.bincount(row, minlength=nRow) == 0).sum())
+    assert abs(st["rowVar"] - ref["rowVar"]) <= 1e-9 * max(1.0, ref["rowVar"])
+    fmt, opts = d.recommend()
+    assert fmt == expect, (fmt, opts, st)
+
+
+def test_recommend_rules_at_baseline_scale(sp):
+    """The rule table on the BASELINE.json shapes, from their closed-form statistics (no 500 M-entry matrix needed)."""
+    import ctypes as C
+    from singlespmv_b200._lib import Options, Stats, lib
+    def rec(**kw):
+        st = Stats()
+        for k, v in kw.items():
+            setattr(st, k, v)
+        o = Options()
+        f = lib.b200spmv_recommend_format(C.byref(st), C.byref(o))
+        return [k for k, v in sp.FORMATS.items() if v == f][0], o.n_block
+    n2 = 1 << 24
+    assert rec(nRow=n2, nCol=n2, nnz=n2 * 32, rowMax=32, rowMin=32, rowMean=32.0, rowVar=0.0, nDiag=2 * n2 - 1) == ("css", 3)   # c2
+    assert rec(nRow=1 << 23, nCol=1 << 23, nnz=258673573, rowMax=400000, rowMean=30.8, rowVar=1e5, nDiag=1 << 24)[0] == "csr5"  # c3
+    assert rec(nRow=256 ** 3, nCol=256 ** 3, nnz=766 ** 3, rowMax=27, rowMean=26.8, rowVar=0.5, nDiag=27)[0] == "dia"           # c4
+    assert rec(nRow=512 ** 3, nCol=512 ** 3, nnz=937951232, rowMax=7, rowMean=6.99, rowVar=0.01, nDiag=7)[0] == "dia"           # c5
+    assert rec(nRow=1000, nCol=1000, nnz=9000, rowMax=40, rowMean=9.0, rowVar=20.0, nDiag=900)[0] == "crs"
