@@ -15,8 +15,11 @@
 // in the reference's operation order, so y is bit-identical to the reference's SS/CSS result (this
 // is how the schedule arrays are proven to be functionally right, not just equal).
 // CSS runs one tile-stream pass per column block, accumulating into y in block order; with the
-// block's slice of x resident in L2 (that is the point of the format, opt_css.cpp:33-45).
+// block's slice of x resident in L2 (that is the point of the format, opt_css.cpp:33-45).  x is protected by the
+// per-load evict_last policy; a persisting-L2 stream access-policy window instead was measured 8 % slower
+// (profiles/r1_experiments.md).
 #include <algorithm>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "tile_stream.cuh"
