@@ -15,7 +15,8 @@ int b2::xload_mode()
     return m;
 }
 
-constexpr int B200SPMV_HOST_CHUNKS = 4;
+constexpr int B200SPMV_HOST_CHUNKS = 8;
+constexpr int B200SPMV_HOST_SLICES = 64;
 
 struct b200spmv_matrix {
     int format = 0;
@@ -24,13 +25,16 @@ struct b200spmv_matrix {
     bool converted = false;
     // staging for host-semantics multiply
     DevBuf<double> x_stage, y_stage;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     cudaEvent_t chunk_done[B200SPMV_HOST_CHUNKS] = {};
+    cudaEvent_t slice_in[B200SPMV_HOST_SLICES] = {};
     ~b200spmv_matrix()
     {
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (in_stream) cudaStreamDestroy(in_stream);
         for (auto e : chunk_done) if (e) cudaEventDestroy(e);
+        for (auto e : slice_in) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -208,14 +212,30 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
     if (!m->stream) {
         B2_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         B2_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        B2_CUDA(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
         for (auto &e : m->chunk_done) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : m->slice_in) B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     if (m->x_stage.n != (size_t)f->nCol) B2_TRY(m->x_stage.alloc((size_t)f->nCol));
     if (m->y_stage.n != (size_t)f->nRow) B2_TRY(m->y_stage.alloc((size_t)f->nRow));
-    B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
-    // Row chunks: the D2H copy of a finished chunk of y overlaps the multiply of the next one (the
-    // reference's cuSPARSE plugin serialises H2D, multiply, D2H: src/opt_cusparse.cpp:72-82).
-    const int nChunks = (f->has_rows() && f->nRow >= (1 << 20)) ? B200SPMV_HOST_CHUNKS : 1;
+    // The reference's cuSPARSE plugin serialises H2D x, multiply, D2H y (src/opt_cusparse.cpp:72-82).  Here the
+    // three overlap where the format allows it: x goes up in the column slices the format consumes one after the
+    // other (CSS: one per column block), rows are multiplied in chunks, and the D2H copy of a finished chunk of y
+    // runs under the next chunk's multiply (PCIe is full duplex: separate in / out streams).
+    const bool big = f->nRow >= (1 << 20);
+    const int nSlices = (big && f->has_rows() && f->n_x_slices() <= B200SPMV_HOST_SLICES) ? f->n_x_slices() : 1;
+    const int nChunks = (big && f->has_rows()) ? B200SPMV_HOST_CHUNKS : 1;
+    if (nSlices == 1) {
+        B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
+    } else {
+        for (int i = 0; i < nSlices; i++) {
+            long long c0, c1;
+            f->x_slice(i, &c0, &c1);
+            if (c1 > c0)
+                B2_CUDA(cudaMemcpyAsync(m->x_stage.p + c0, x_h + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, m->in_stream));
+            B2_CUDA(cudaEventRecord(m->slice_in[i], m->in_stream));
+        }
+    }
     if (nChunks == 1) {
         B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
         B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
@@ -223,8 +243,16 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
         return B200SPMV_OK;
     }
     for (int c = 0; c < nChunks; c++) {
-        const int rb = (int)((long long)f->nRow * c / nChunks) & ~31, re = c + 1 == nChunks ? f->nRow : (int)((long long)f->nRow * (c + 1) / nChunks) & ~31;
-        B2_TRY(f->multiply_rows(rb, re, m->x_stage.p, m->y_stage.p, m->stream));
+        const int rb = (int)((long long)f->nRow * c / nChunks) & ~31;
+        const int re = c + 1 == nChunks ? f->nRow : (int)((long long)f->nRow * (c + 1) / nChunks) & ~31;
+        if (nSlices == 1) {
+            B2_TRY(f->multiply_rows(rb, re, m->x_stage.p, m->y_stage.p, m->stream));
+        } else {
+            for (int i = 0; i < nSlices; i++) {
+                if (c == 0) B2_CUDA(cudaStreamWaitEvent(m->stream, m->slice_in[i], 0));
+                B2_TRY(f->multiply_rows_slice(i, rb, re, m->x_stage.p, m->y_stage.p, m->stream));
+            }
+        }
         B2_CUDA(cudaEventRecord(m->chunk_done[c], m->stream));
         B2_CUDA(cudaStreamWaitEvent(m->copy_stream, m->chunk_done[c], 0));
         B2_CUDA(cudaMemcpyAsync(y_h + rb, m->y_stage.p + rb, sizeof(double) * (size_t)(re - rb), cudaMemcpyDeviceToHost, m->copy_stream));

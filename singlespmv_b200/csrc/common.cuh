@@ -88,6 +88,12 @@ struct Format {
         return B200SPMV_ERR_UNSUPPORTED;
     }
     virtual bool has_rows() const { return false; }      // multiply_rows available (host-semantics pipeline uses it)
+    // Column slices of x in order of first use (CSS: one per column block; everything else: all of x at once).
+    // multiply_rows_slice(i, ...) adds slice i's contribution to rows [rb, re) (slice 0 overwrites), so the host
+    // pipeline can start multiplying while later slices of x are still crossing PCIe.
+    virtual int n_x_slices() const { return 1; }
+    virtual void x_slice(int, long long *c0, long long *c1) const { *c0 = 0; *c1 = nCol; }
+    virtual int multiply_rows_slice(int, int rb, int re, const double *x, double *y, cudaStream_t s) { return multiply_rows(rb, re, x, y, s); }
     // format-specific scalars/arrays; return false / -1 when the name is unknown
     virtual bool scalar(const std::string &name, long long *out) = 0;
     virtual long long array(const std::string &name, void *dst_h, long long dst_bytes) = 0;

@@ -19,17 +19,13 @@ constexpr int COO_IPT = 8;
 constexpr int COO_TILE = COO_THREADS * COO_IPT;
 constexpr int COO_LONG = 64;
 constexpr int COO_MAXLONG = COO_TILE / COO_LONG + 2;
-// products live at a padded index (2 doubles per 16): threads own 8 consecutive entries, and an unpadded stride of
-// 8 doubles would put every other lane on the same bank (ncu: 200 M conflicts, short-scoreboard/MIO-bound kernel)
-__device__ __forceinline__ int coo_pad(int i) { return i + 2 * (i >> 4); }
-constexpr int COO_PROD = COO_TILE + 2 * (COO_TILE >> 4);
 
 __global__ void __launch_bounds__(COO_THREADS)
 coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
                 const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
                 int vec_ok)
 {
-    __shared__ __align__(16) double prod[COO_PROD];
+    __shared__ __align__(16) double prod[COO_TILE];
     __shared__ __align__(16) int srow[COO_TILE];
     __shared__ unsigned head[COO_TILE / 32 + 1];     // bit i = entry i starts a run of equal row ids
     __shared__ int long_start[COO_MAXLONG];
@@ -52,7 +48,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
             const double2 v0 = ld_stream_d2(val + t0 + o, pol_stream), v1 = ld_stream_d2(val + t0 + o + 2, pol_stream);
             const double x0 = ld_x(x + c.x, pol_x), x1 = ld_x(x + c.y, pol_x), x2 = ld_x(x + c.z, pol_x), x3 = ld_x(x + c.w, pol_x);
             *reinterpret_cast<int4 *>(srow + o) = r;
-            double2 *dst = reinterpret_cast<double2 *>(prod + coo_pad(o));      // o % 4 == 0: the four stay contiguous
+            double2 *dst = reinterpret_cast<double2 *>(prod + o);
             dst[0] = make_double2(__dmul_rn(v0.x, x0), __dmul_rn(v0.y, x1));
             dst[1] = make_double2(__dmul_rn(v1.x, x2), __dmul_rn(v1.y, x3));
             // run starts, in registers: the row id in front of this lane's four entries comes from the lane below
@@ -70,7 +66,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
         for (int i = tid; i < COO_TILE / 32 + 1; i += COO_THREADS) head[i] = 0u;
         for (int i = tid; i < n; i += COO_THREADS) {
             srow[i] = ld_stream_i1(row + t0 + i, pol_stream);
-            prod[coo_pad(i)] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream), ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
+            prod[i] = __dmul_rn(ld_stream_d1(val + t0 + i, pol_stream), ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
         }
     }
     const int prev_row = t0 > 0 ? row[t0 - 1] : -1;
@@ -105,7 +101,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
                 continue;
             }
             double acc = 0.0;
-            for (int j = i; j < end; j++) acc = __dadd_rn(acc, prod[coo_pad(j)]);
+            for (int j = i; j < end; j++) acc = __dadd_rn(acc, prod[j]);
             y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
         }
     }
@@ -121,7 +117,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
         const int b = s < 0 ? 0 : s;
         const int r = srow[b];
         double acc = 0.0;
-        for (int k = b + lane; k < n && srow[k] == r; k += 32) acc += prod[coo_pad(k)];
+        for (int k = b + lane; k < n && srow[k] == r; k += 32) acc += prod[k];
         acc = warp_sum(acc);
         if (lane == 0) {
             if (s < 0) carry[t] = acc;

@@ -479,6 +479,19 @@ struct CssFormat : Format {
         return B200SPMV_OK;
     }
 
+    int n_x_slices() const override { return faithful || nBlock < 1 ? 1 : nBlock; }
+    void x_slice(int i, long long *c0, long long *c1) const override
+    {
+        if (faithful || nBlock < 1) { *c0 = 0; *c1 = nCol; return; }
+        *c0 = (long long)i * B;
+        *c1 = std::min<long long>(nCol, *c0 + B);
+    }
+    int multiply_rows_slice(int i, int rb, int re, const double *x, double *y, cudaStream_t s) override
+    {
+        if (faithful || nBlock < 1) return multiply_rows(rb, re, x, y, s);
+        return blocks[(size_t)i]->ts.run_rows(x, y, i > 0, rb, re, s);
+    }
+
     bool scalar(const std::string &n, long long *out) override
     {
         if (n == "B") { *out = B; return true; }

@@ -47,7 +47,7 @@ __device__ __forceinline__ double ld_val1(const float *p, uint64_t pol)
     return (double)r;
 }
 
-template <typename VT, int XM>
+template <typename VT>
 __global__ void __launch_bounds__(TS_THREADS)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const int *__restrict__ tile_row,
@@ -79,10 +79,10 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         double xs[TS_IPT];
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
-            xs[4 * k + 0] = ld_x_mode<XM>(x + c[k].x, pol_x);
-            xs[4 * k + 1] = ld_x_mode<XM>(x + c[k].y, pol_x);
-            xs[4 * k + 2] = ld_x_mode<XM>(x + c[k].z, pol_x);
-            xs[4 * k + 3] = ld_x_mode<XM>(x + c[k].w, pol_x);
+            xs[4 * k + 0] = ld_x(x + c[k].x, pol_x);
+            xs[4 * k + 1] = ld_x(x + c[k].y, pol_x);
+            xs[4 * k + 2] = ld_x(x + c[k].z, pol_x);
+            xs[4 * k + 3] = ld_x(x + c[k].w, pol_x);
         }
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
@@ -123,9 +123,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     }
     __syncthreads();
 
-    // ---- phase 2b: rows above TS_LONG entries: a whole warp for the very long ones and for the carried-in
-    // piece, a sub-warp of TS_SUB lanes for the rest (medium rows would otherwise leave most threads idle
-    // behind a few long sequential sums: a 27-point stencil has 76 rows per tile for 256 threads)
+    // ---- phase 2b: one warp per long row / carried-in piece
     const int lane = tid & 31, warp = tid >> 5;
     const int nl = n_long;
     for (int i = warp; i < nl; i += TS_THREADS / 32) {
@@ -137,7 +135,6 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         } else {
             b = row_ptr[r];
             e = min(row_ptr[r + 1], t1);
-            if (e - b <= TS_WARP_ROW) continue;               // medium: sub-warp pass below
         }
         double acc = 0.0;
         for (int j = b + lane; j < e; j += 32) acc += prod[j - t0];
@@ -146,22 +143,6 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
             if (r < 0) carry[t] = acc;
             else y[r] = accumulate ? y[r] + acc : acc;
         }
-    }
-    const int sub = tid / TS_SUB, sl = tid % TS_SUB;
-    for (int i0 = 0; i0 < nl; i0 += TS_THREADS / TS_SUB) {    // uniform trip count: the shuffles below are warp-wide
-        const int i = i0 + sub;
-        const int r = i < nl ? long_row[i] : -1;
-        int b = 0, e = 0;
-        if (r >= 0) {
-            b = row_ptr[r];
-            e = min(row_ptr[r + 1], t1);
-            if (e - b > TS_WARP_ROW) e = b;                   // done by a warp above
-        }
-        double acc = 0.0;
-        for (int j = b + sl; j < e; j += TS_SUB) acc += prod[j - t0];
-#pragma unroll
-        for (int o = TS_SUB / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (sl == 0 && e > b) y[r] = accumulate ? y[r] + acc : acc;
     }
 }
 
@@ -249,11 +230,11 @@ int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int 
     const bool fix = nT > 1 || tileLo > 0;
     if (f32) {
         const float *v = static_cast<const float *>(val);
-        tile_stream_kernel<float, 0><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
+        tile_stream_kernel<float><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
         if (fix) tile_fixup_kernel<float><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
     } else {
         const double *v = static_cast<const double *>(val);
-        tile_stream_kernel<double, 0><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
+        tile_stream_kernel<double><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
         if (fix) tile_fixup_kernel<double><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
     }
     B2_KERNEL_CHECK();

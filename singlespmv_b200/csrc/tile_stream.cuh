@@ -8,8 +8,8 @@
 //      materialises them in val_buf, src/opt_ss.cpp:226-238, costing +16 B/nnz);
 //   2. reduces the rows it OWNS (rows whose first entry lies in the tile) with an in-tile row-bin
 //      scheduler: short rows one thread each, sequentially in ascending column order with
-//      unfused mul/add (bit-identical to reference src/opt_crs.cpp:61-67); medium rows 8 lanes each, long
-//      rows one warp each (lanes stride, shuffle tree); the piece of a row carried in from the previous tile
+//      unfused mul/add (bit-identical to reference src/opt_crs.cpp:61-67); long rows one warp
+//      each (lanes stride, shuffle tree); the piece of a row carried in from the previous tile
 //      is reduced by a warp into carry[tile].
 // A second, tiny kernel finishes rows that cross tile boundaries: short ones are recomputed
 // sequentially (so EVERY row up to TS_LONG entries is bit-exact), long ones get their carries
@@ -18,7 +18,8 @@
 // Variants measured and rejected on B200 (profiles/r1_call8_9_summary.md): scalar lane-contiguous loads (-20 %:
 // 24 instead of 14 load instructions per thread), row_ptr staged in shared memory + warp-local long rows
 // (-15 %: 40 registers -> 6 instead of 8 resident CTAs), cp.async.bulk.prefetch.L2 of the tile a later wave will
-// stream (-4 % to -27 % with distance).  Resident CTAs x 24 KB in flight is what feeds HBM.
+// stream (-4 % to -27 % with distance), 8-lane sub-warps for rows of 17-256 entries (c4: -26 %).
+// Resident CTAs x 24 KB in flight is what feeds HBM.
 #pragma once
 #include <map>
 
@@ -29,9 +30,7 @@ namespace b2 {
 constexpr int TS_THREADS = 256;
 constexpr int TS_IPT = 8;
 constexpr int TS_TILE = TS_THREADS * TS_IPT;   // 2048 non-zeros = 24 KB of matrix per CTA
-constexpr int TS_LONG = 16;                    // rows up to this many entries: one thread, sequential, bit-exact
-constexpr int TS_SUB = 8;                      // lanes per medium row (TS_LONG < entries <= TS_WARP_ROW)
-constexpr int TS_WARP_ROW = 256;               // longer rows (in the tile) take a whole warp
+constexpr int TS_LONG = 64;                    // rows longer than this are reduced by a warp
 constexpr int TS_MAXLONG = TS_TILE / TS_LONG + 2;
 
 struct TileStream {
