@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" surface declared in include/b200spmv.h.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -222,9 +223,11 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
     // three overlap where the format allows it: x goes up in the column slices the format consumes one after the
     // other (CSS: one per column block), rows are multiplied in chunks, and the D2H copy of a finished chunk of y
     // runs under the next chunk's multiply (PCIe is full duplex: separate in / out streams).
+    static const int env_chunks = getenv("B200SPMV_HOST_CHUNKS") ? atoi(getenv("B200SPMV_HOST_CHUNKS")) : B200SPMV_HOST_CHUNKS;
+    static const int env_slices = getenv("B200SPMV_HOST_SLICES") ? atoi(getenv("B200SPMV_HOST_SLICES")) : 1;
     const bool big = f->nRow >= (1 << 20);
-    const int nSlices = (big && f->has_rows() && f->n_x_slices() <= B200SPMV_HOST_SLICES) ? f->n_x_slices() : 1;
-    const int nChunks = (big && f->has_rows()) ? B200SPMV_HOST_CHUNKS : 1;
+    const int nSlices = (env_slices && big && f->has_rows() && f->n_x_slices() <= B200SPMV_HOST_SLICES) ? f->n_x_slices() : 1;
+    const int nChunks = (big && f->has_rows()) ? std::max(1, std::min(env_chunks, B200SPMV_HOST_CHUNKS)) : 1;
     if (nSlices == 1) {
         B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
     } else {

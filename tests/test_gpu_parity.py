@@ -593,3 +593,75 @@ def test_recommend_rules_at_baseline_scale(sp):
     assert rec(nRow=256 ** 3, nCol=256 ** 3, nnz=766 ** 3, rowMax=27, rowMean=26.8, rowVar=0.5, nDiag=27)[0] == "dia"           # c4
     assert rec(nRow=512 ** 3, nCol=512 ** 3, nnz=937951232, rowMax=7, rowMean=6.99, rowVar=0.01, nDiag=7)[0] == "dia"           # c5
     assert rec(nRow=1000, nCol=1000, nnz=9000, rowMax=40, rowMean=9.0, rowVar=20.0, nDiag=900)[0] == "crs"
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json full sizes
+def _mult(m, x, n):
+    import torch
+    y = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    m.multiply(x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("kind,p0,fmts", [("box3d27", 256, ("dia", "ell", "jds", "crs")),      # config 4
+                                          ("lap3d7", 512, ("crs", "dia", "ell")),               # config 5
+                                          ("lap2d5", 1024, ("crs", "dia", "ell", "jds", "ss", "coo"))])   # config 1
+def test_full_size_stencils(sp, kind, p0, fmts):
+    """At BASELINE.json's full sizes the oracle is too slow; size-independent properties instead:
+    * A.1 has a closed form for the stencils (diagonal = points-1, off-diagonals = -1): y_i = points - count_i,
+      an exact small integer -> checks every row of every format;
+    * every format that sums a row in ascending column order must agree bit for bit on a random x;
+    * linearity A(2x + z/2) = 2Ax + Az/2."""
+    import torch
+    d = sp.DeviceCoo(kind, p0)
+    n = d.nRow
+    stats, _ = d.analyze()
+    points = {"lap2d5": 5, "lap3d7": 7, "box3d27": 27}[kind]
+    assert stats["rowMax"] == points and stats["nDiag"] == points and stats["nEmptyRows"] == 0
+    mats = {f: sp.SpMatOpt(f).convert_device(d) for f in fmts}
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    z = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    # count_i = entries of row i, closed form of the generator (no wrap-around at the grid border)
+    idx = torch.arange(n, device="cuda")
+    span = lambda a: 1 + (a > 0).long() + (a < p0 - 1).long()
+    if kind == "lap2d5":
+        counts = span(idx // p0) + span(idx % p0) - 1
+    else:
+        si, sj, sk = span(idx // (p0 * p0)), span((idx // p0) % p0), span(idx % p0)
+        counts = si + sj + sk - 2 if kind == "lap3d7" else si * sj * sk
+    assert int(counts.sum().item()) == d.nNnz
+    counts = counts.double()
+    del idx
+    ys = {}
+    for f, m in mats.items():
+        y1 = _mult(m, ones, n)
+        assert torch.equal(y1, points - counts), f
+        ys[f] = _mult(m, x, n)
+        lin = _mult(m, 2.0 * x + 0.5 * z, n)
+        assert torch.allclose(lin, 2.0 * ys[f] + 0.5 * _mult(m, z, n), rtol=1e-12, atol=1e-12), f
+    first = fmts[0]
+    for f in fmts[1:]:
+        assert torch.equal(ys[f], ys[first]), (f, first)
+
+
+def test_full_size_uniform_and_rmat(sp):
+    """Configs 2 and 3 at full size: formats agree with each other within the tolerance, A.1 = row sums of val."""
+    import torch
+    for kind, p0, p1, seed, fmts, opts in (("uniform", 1 << 24, 32, 1, ("ell", "css", "jds"), {"css": {"n_block": 3}}),
+                                           ("rmat", 23, 1 << 28, 42, ("crs", "csr5", "coo"), {})):
+        d = sp.DeviceCoo(kind, p0, p1, seed)
+        n = d.nRow
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        ys = []
+        for f in fmts:
+            m = sp.SpMatOpt(f, **opts.get(f, {})).convert_device(d)
+            ys.append(_mult(m, x, n))
+            m.destroy()
+        # values and x are in [0,1): sum_j |a_ij x_j| = y_i, so the tolerance is relative to y itself
+        for y in ys[1:]:
+            assert torch.all((y - ys[0]).abs() <= 1e-12 * ys[0].abs() + 1e-300)
+        d.free()
