@@ -227,7 +227,10 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
     static const int env_slices = getenv("B200SPMV_HOST_SLICES") ? atoi(getenv("B200SPMV_HOST_SLICES")) : 1;
     const bool big = f->nRow >= (1 << 20);
     const int nSlices = (env_slices && big && f->has_rows() && f->n_x_slices() <= B200SPMV_HOST_SLICES) ? f->n_x_slices() : 1;
-    const int nChunks = (big && f->has_rows()) ? std::max(1, std::min(env_chunks, B200SPMV_HOST_CHUNKS)) : 1;
+    // measured on c2 (profiles/r1_experiments.md): formats that stream all of x per pass gain from 8 row chunks;
+    // CSS pays for every chunk with another round of x-slice switches in L2 and is best with 2
+    int nChunks = (big && f->has_rows()) ? std::max(1, std::min(env_chunks, B200SPMV_HOST_CHUNKS)) : 1;
+    if (nSlices > 1 && !getenv("B200SPMV_HOST_CHUNKS")) nChunks = 2;
     if (nSlices == 1) {
         B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
     } else {
@@ -239,7 +242,7 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
             B2_CUDA(cudaEventRecord(m->slice_in[i], m->in_stream));
         }
     }
-    if (nChunks == 1) {
+    if (nChunks == 1 && nSlices == 1) {
         B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
         B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
         B2_CUDA(cudaStreamSynchronize(m->stream));
