@@ -132,6 +132,11 @@ def cpu_reference_crs(nRow, nCol, row, col, val, x, min_seconds, max_calls, warm
     import numpy as np
     import oracle_lib
     times = []
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(cpu_threads()))
+    except OSError:
+        pass
     if oracle_lib.ref_available("crs"):
         kind = "reference"
         p = oracle_lib.RefPlugin("crs")
@@ -195,6 +200,7 @@ def run_reference_arm(args, wl, wl_key):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(cpu_threads())        # before libgomp initialises
     rows = sample_rows_for(wl, args.mini)
     nRow, nCol, row, col, val, x = host_sample(wl, rows)
     kind, times = cpu_reference_crs(nRow, nCol, row, col, val, x, 0, 0, warmup=args.warmup, exact_calls=args.steps)

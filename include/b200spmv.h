@@ -65,7 +65,8 @@ typedef enum {
 typedef struct {
     int segment_width;   /* SS/CSS: SEGMENT_WIDTH (W), power of two; default 4 (= ALIGNMENT/8, ALIGNMENT=32) */
     int n_block;         /* CSS: N_BLOCK; default 1 */
-    int csr5_sigma;      /* CSR5: sigma; 0 = auto (anonymouslib_cuda.h:293-317) */
+    int csr5_sigma;      /* CSR5: sigma 1..32; -1 = upstream's auto rule (anonymouslib_cuda.h:293-317);
+                            0 = the same rule with a floor of 16 (tuned on B200) */
     int ss_faithful;     /* SS/CSS: 1 = three-phase Mul/fold/gather with val_buf, the reference's
                             operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
     int value_f32;       /* CRS: 1 = store the matrix values as fp32 (rounded once at conversion); x, y and all

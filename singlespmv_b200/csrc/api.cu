@@ -112,7 +112,7 @@ int b200spmv_create(int format, const b200spmv_options *opts, b200spmv_matrix **
         set_error("create: segment_width=%d must be a power of two (reference src/opt_ss.cpp:272 masks with W-1)", o.segment_width);
         return B200SPMV_ERR_INVALID;
     }
-    if (o.n_block < 1 || o.csr5_sigma < 0 || o.csr5_sigma > 32) {
+    if (o.n_block < 1 || o.csr5_sigma < -1 || o.csr5_sigma > 32) {
         set_error("create: bad option (n_block=%d csr5_sigma=%d)", o.n_block, o.csr5_sigma);
         return B200SPMV_ERR_INVALID;
     }

@@ -299,9 +299,12 @@ struct Csr5Format : Format {
         nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
         B2_TRY(validate_sorted_coo(A, s));
         sigma = sigma_opt;
-        if (sigma == 0) {                                   // anonymouslib_cuda.h:293-317
+        if (sigma <= 0) {                                   // upstream's auto-tuning rule, anonymouslib_cuda.h:293-317
             const int per_row = nRow > 0 ? nnz / nRow : 0;
             sigma = per_row <= 4 ? 4 : per_row <= 32 ? per_row : per_row <= 256 ? 32 : 6;
+            // 0 = tuned for B200: a warp needs at least 16 entries per lane in flight (c5, 7 nnz/row: sigma 6 -> 492,
+            // sigma 16 -> 690 GFLOP/s); -1 = upstream's rule verbatim
+            if (sigma_opt == 0 && sigma < 16) sigma = 16;
         }
         int base = 2;                                       // anonymouslib_cuda.h:121-137
         bit_y = 1;

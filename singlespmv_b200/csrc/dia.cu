@@ -12,6 +12,8 @@
 // 1-D TMA bulk copy (cp.async.bulk + mbarrier transaction count), so a 27-point stencil pulls 9
 // windows from L2 instead of 27.  Per row the diagonals are accumulated in ascending order with
 // unfused mul/add = the reference's order (and, padding zeros aside, opt_crs.cpp's) -> bit-identical y.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -115,7 +117,8 @@ __device__ __forceinline__ DiaWindow dia_window(int row0, int off, int cnt, int 
 }
 
 // ---------------------------------------------------------------- multiply, TMA-staged x
-__global__ void __launch_bounds__(DIA_THREADS, 6)
+template <int DU, int MINB>
+__global__ void __launch_bounds__(DIA_THREADS, MINB)
 dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const DiaRuns runs,
                     const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int nCol)
 {
@@ -172,7 +175,7 @@ dia_spmv_tma_kernel(const double *__restrict__ diag, size_t ld, int nDiag, const
     if (rows == DIA_R) {
         // DIA_U x DIA_RPT independent 8-byte loads per thread per round; enough CTAs stay resident
         // (launch bounds below) that no software double buffer is needed
-        constexpr int U = DIA_U;
+        constexpr int U = DU;
         double d[U][DIA_RPT];
         int p = 0;
 #pragma unroll
@@ -318,8 +321,12 @@ struct DiaFormat : Format {
             }
             smem_bytes = (size_t)soff * sizeof(double);
             if (smem_bytes > 200 * 1024) tma_ok = false;
-            else if (smem_bytes > 48 * 1024)
-                B2_CUDA(cudaFuncSetAttribute(dia_spmv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            else if (smem_bytes > 48 * 1024) {
+                B2_CUDA(cudaFuncSetAttribute(dia_spmv_tma_kernel<5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+                B2_CUDA(cudaFuncSetAttribute(dia_spmv_tma_kernel<7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+                B2_CUDA(cudaFuncSetAttribute(dia_spmv_tma_kernel<9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+                B2_CUDA(cudaFuncSetAttribute(dia_spmv_tma_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            }
         }
         return B200SPMV_OK;
     }
@@ -335,8 +342,14 @@ struct DiaFormat : Format {
             B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
             return B200SPMV_OK;
         }
-        if (tma_ok && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-            dia_spmv_tma_kernel<<<ceil_div(re - rb, DIA_R), DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
+        static const int du = getenv("B200SPMV_DIA_U") ? atoi(getenv("B200SPMV_DIA_U")) : DIA_U;
+        if (tma_ok && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const int grid = ceil_div(re - rb, DIA_R);
+            if (du == 7) dia_spmv_tma_kernel<7, 5><<<grid, DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
+            else if (du == 9) dia_spmv_tma_kernel<9, 4><<<grid, DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
+            else if (du == 3) dia_spmv_tma_kernel<3, 8><<<grid, DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
+            else dia_spmv_tma_kernel<5, 6><<<grid, DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
+        }
         else
             dia_spmv_direct_kernel<<<ceil_div(re - rb, DIA_THREADS), DIA_THREADS, 0, s>>>(diag.p, ld, nDiag, ioff.p, x, y, rb, re, nRow, nCol);
         B2_KERNEL_CHECK();

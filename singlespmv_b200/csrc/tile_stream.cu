@@ -9,7 +9,7 @@ namespace b2 {
 // tile_row[t] = first row r with row_ptr[r] >= t*TS_TILE (lower bound over row_ptr[0..nRow]).
 // Rows [tile_row[t], tile_row[t+1]) are OWNED by tile t: their first entry lies in it.  Empty
 // rows are owned by the tile that contains their (shared) position; trailing rows by the last.
-__global__ void tile_row_kernel(const int *__restrict__ ptr, int nRow, int nTiles, int *__restrict__ tile_row)
+__global__ void tile_row_kernel(const int *__restrict__ ptr, int nRow, int nTiles, int tile, int *__restrict__ tile_row)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > nTiles) return;
@@ -17,7 +17,7 @@ __global__ void tile_row_kernel(const int *__restrict__ ptr, int nRow, int nTile
         tile_row[t] = nRow;
         return;
     }
-    int key = t * TS_TILE, lo = 0, hi = nRow + 1;
+    int key = t * tile, lo = 0, hi = nRow + 1;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (ptr[mid] < key) lo = mid + 1;
@@ -47,32 +47,33 @@ __device__ __forceinline__ double ld_val1(const float *p, uint64_t pol)
     return (double)r;
 }
 
-template <typename VT>
-__global__ void __launch_bounds__(TS_THREADS)
+template <typename VT, int TH>
+__global__ void __launch_bounds__(TH)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const int *__restrict__ tile_row,
                    const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
                    int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok)
 {
-    __shared__ __align__(16) double prod[TS_TILE];
-    __shared__ int long_row[TS_MAXLONG];
+    constexpr int TILE = TH * TS_IPT;
+    __shared__ __align__(16) double prod[TILE];
+    __shared__ int long_row[TILE / TS_LONG + 2];
     __shared__ int n_long;
 
     const int tid = threadIdx.x;
     const int t = tileLo + blockIdx.x;
-    const int t0 = t * TS_TILE;
-    const int t1 = min(t0 + TS_TILE, nnz);
+    const int t0 = t * TILE;
+    const int t1 = min(t0 + TILE, nnz);
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t pol_x = policy_evict_last();
     if (tid == 0) n_long = 0;
 
     // ---- phase 1: stream the tile, gather x, park products in shared memory
-    if (t1 - t0 == TS_TILE && vec_ok) {
+    if (t1 - t0 == TILE && vec_ok) {
         int4 c[TS_IPT / 4];
         double2 v[TS_IPT / 2];
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
-            const int e = t0 + 4 * (tid + k * TS_THREADS);
+            const int e = t0 + 4 * (tid + k * TH);
             c[k] = ld_stream_i4(col + e, pol_stream);
             ld_val4(val + e, pol_stream, v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
         }
@@ -86,13 +87,13 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         }
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
-            double2 *dst = reinterpret_cast<double2 *>(prod + 4 * (tid + k * TS_THREADS));
+            double2 *dst = reinterpret_cast<double2 *>(prod + 4 * (tid + k * TH));
             dst[0] = make_double2(__dmul_rn(v[2 * k].x, xs[4 * k]), __dmul_rn(v[2 * k].y, xs[4 * k + 1]));
             dst[1] = make_double2(__dmul_rn(v[2 * k + 1].x, xs[4 * k + 2]),
                                   __dmul_rn(v[2 * k + 1].y, xs[4 * k + 3]));
         }
     } else {
-        for (int i = tid; i < t1 - t0; i += TS_THREADS)
+        for (int i = tid; i < t1 - t0; i += TH)
             prod[i] = __dmul_rn(ld_val1(val + t0 + i, pol_stream),
                                 ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
     }
@@ -103,7 +104,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     __syncthreads();
 
     // ---- phase 2a: one thread per owned row, in-tile row-bin scheduler
-    for (int r = r_lo + tid; r < r_hi; r += TS_THREADS) {
+    for (int r = r_lo + tid; r < r_hi; r += TH) {
         if (r < rowLo || r >= rowHi) continue;
         const int b = row_ptr[r], e_full = row_ptr[r + 1];
         const int e = min(e_full, t1);
@@ -126,7 +127,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     // ---- phase 2b: one warp per long row / carried-in piece
     const int lane = tid & 31, warp = tid >> 5;
     const int nl = n_long;
-    for (int i = warp; i < nl; i += TS_THREADS / 32) {
+    for (int i = warp; i < nl; i += TH / 32) {
         const int r = long_row[i];
         int b, e;
         if (r < 0) {
@@ -153,24 +154,24 @@ __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__
                                   const VT *__restrict__ val, const int *__restrict__ tile_row,
                                   const double *__restrict__ x, double *__restrict__ y,
                                   const double *__restrict__ carry, int tileLo, int tileHi, int rowLo,
-                                  int rowHi, int accumulate)
+                                  int rowHi, int accumulate, int tile)
 {
     const int t = tileLo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= tileHi || t == 0) return;
-    const int t0 = t * TS_TILE;
+    const int t0 = t * tile;
     const int r0 = tile_row[t];
     const int e = row_ptr[r0];
     if (e <= t0) return;                       // a row starts exactly at the tile start
     const int rc = r0 - 1;
     if (rc < rowLo || rc >= rowHi) return;
     const int b = row_ptr[rc];
-    if (t != b / TS_TILE + 1) return;
+    if (t != b / tile + 1) return;
     if (e - b <= TS_LONG) {
         double acc = 0.0;
         for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn((double)val[j], x[col[j]]));
         y[rc] = accumulate ? __dadd_rn(y[rc], acc) : acc;
     } else {
-        const int last = (e - 1) / TS_TILE;
+        const int last = (e - 1) / tile;
         double sum = 0.0;
         for (int u = t; u <= last; u++) sum += carry[u];
         y[rc] += sum;
@@ -186,10 +187,13 @@ int TileStream::build(const int *row_ptr_d, const int *col_d, const void *val_d,
     val = val_d;
     nRow = nRow_;
     nnz = nnz_;
-    nTiles = ceil_div(nnz, TS_TILE);
+    static const int env_threads = getenv("B200SPMV_TS_THREADS") ? atoi(getenv("B200SPMV_TS_THREADS")) : 256;
+    threads = (env_threads == 64 || env_threads == 128 || env_threads == 512) ? env_threads : 256;
+    tile = threads * TS_IPT;
+    nTiles = ceil_div(nnz, tile);
     B2_TRY(tile_row.alloc((size_t)nTiles + 1));
     B2_TRY(carry.alloc((size_t)nTiles));
-    tile_row_kernel<<<ceil_div(nTiles + 1, 256), 256, 0, s>>>(row_ptr, nRow, nTiles, tile_row.p);
+    tile_row_kernel<<<ceil_div(nTiles + 1, 256), 256, 0, s>>>(row_ptr, nRow, nTiles, tile, tile_row.p);
     B2_KERNEL_CHECK();
     range_cache.clear();
     return B200SPMV_OK;
@@ -210,8 +214,8 @@ int TileStream::run_rows(const double *x, double *y, bool accumulate, int rb, in
         int pb = 0, pe = 0;
         B2_CUDA(cudaMemcpy(&pb, row_ptr + rb, sizeof(int), cudaMemcpyDeviceToHost));
         B2_CUDA(cudaMemcpy(&pe, row_ptr + re, sizeof(int), cudaMemcpyDeviceToHost));
-        const int lo = nTiles ? std::min(pb / TS_TILE, nTiles - 1) : 0;
-        const int hi = std::min(nTiles, pe / TS_TILE + 1);
+        const int lo = nTiles ? std::min(pb / tile, nTiles - 1) : 0;
+        const int hi = std::min(nTiles, pe / tile + 1);
         it = range_cache.emplace(key, std::make_pair(lo, hi)).first;
     }
     return run(x, y, accumulate, rb, re, it->second.first, it->second.second, s);
@@ -228,14 +232,23 @@ int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int 
     const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
     const int nT = tileHi - tileLo, acc = accumulate ? 1 : 0;
     const bool fix = nT > 1 || tileLo > 0;
+#define TS_LAUNCH(VT, TH, v)                                                                                                      \
+    do {                                                                                                                          \
+        tile_stream_kernel<VT, TH><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
+        if (fix) tile_fixup_kernel<VT><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc, tile); \
+    } while (0)
     if (f32) {
         const float *v = static_cast<const float *>(val);
-        tile_stream_kernel<float><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
-        if (fix) tile_fixup_kernel<float><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
+        if (threads == 64) TS_LAUNCH(float, 64, v);
+        else if (threads == 128) TS_LAUNCH(float, 128, v);
+        else if (threads == 512) TS_LAUNCH(float, 512, v);
+        else TS_LAUNCH(float, 256, v);
     } else {
         const double *v = static_cast<const double *>(val);
-        tile_stream_kernel<double><<<nT, TS_THREADS, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok);
-        if (fix) tile_fixup_kernel<double><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc);
+        if (threads == 64) TS_LAUNCH(double, 64, v);
+        else if (threads == 128) TS_LAUNCH(double, 128, v);
+        else if (threads == 512) TS_LAUNCH(double, 512, v);
+        else TS_LAUNCH(double, 256, v);
     }
     B2_KERNEL_CHECK();
     return B200SPMV_OK;

@@ -18,7 +18,8 @@
 // Variants measured and rejected on B200 (profiles/r1_call8_9_summary.md): scalar lane-contiguous loads (-20 %:
 // 24 instead of 14 load instructions per thread), row_ptr staged in shared memory + warp-local long rows
 // (-15 %: 40 registers -> 6 instead of 8 resident CTAs), cp.async.bulk.prefetch.L2 of the tile a later wave will
-// stream (-4 % to -27 % with distance), 8-lane sub-warps for rows of 17-256 entries (c4: -26 %).
+// stream (-4 % to -27 % with distance), 8-lane sub-warps for rows of 17-256 entries (c4: -26 %), CTA widths 64 / 128 / 512 (c5: -9 / -4 / -3 %), a persistent
+// cp.async double-buffered loop at 4 CTAs/SM (c5: -17 %, gather-bound c2/c3: -55 %: the x gathers need the threads).
 // Resident CTAs x 24 KB in flight is what feeds HBM.
 #pragma once
 #include <map>
@@ -42,6 +43,7 @@ struct TileStream {
     int nRow = 0, nnz = 0;
     // owned
     int nTiles = 0;
+    int threads = TS_THREADS, tile = TS_TILE;   // CTA width and entries per tile of this instance
     DevBuf<int> tile_row;           // [nTiles+1]: first row whose first entry is >= tile start
     DevBuf<double> carry;           // [nTiles]
 

@@ -141,11 +141,21 @@ def test_host_multiply_pipeline_large(sp, oracle, fmt, opt):
     nr, nc, row, col, val = oracle.stencil("lap2d5", 1100)
     x = oracle.reference_vectors(nc, nr)[0]
     y_ref = oracle.crs_result(nr, row, col, val, x)
-    _, y = run_host(sp, fmt, nr, nc, row, col, val, x, **opt)
+    A_opt, y = run_host(sp, fmt, nr, nc, row, col, val, x, **opt)
     if fmt == "css":
         assert_y(y, y_ref, row, col, val, x, nr)
     else:
         assert np.array_equal(y, y_ref)
+    # a DIFFERENT x on the same handle: a multiply that starts before its slice of x has landed would still
+    # see the previous vector in the staging buffer
+    for x2 in (x[::-1].copy(), np.full(nc, 0.25), x * 3.0 + 1.0):
+        y2 = np.full(nr, np.nan)
+        A_opt.multiply_host(x2, y2)
+        y2_ref = oracle.crs_result(nr, row, col, val, x2)
+        if fmt == "css":
+            assert_y(y2, y2_ref, row, col, val, x2, nr)
+        else:
+            assert np.array_equal(y2, y2_ref)
 
 
 def test_crs_f32_storage(sp, oracle, all_cases):
@@ -414,9 +424,12 @@ def check_csr5_arrays(A_opt, m, tag):
 def test_csr5(sp, oracle, all_cases):
     for name, nRow, nCol, row, col, val, x in all_cases:
         y_ref = oracle.crs_result(nRow, row, col, val, x)
-        for sigma in (0, 4, 7, 16, 32):
-            m = oracle.csr5_convert(nRow, row, col, val, sigma)
+        for sigma in (-1, 0, 4, 7, 32):
             A_opt, y = run_host(sp, "csr5", nRow, nCol, row, col, val, x, csr5_sigma=sigma)
+            ref_rule = oracle.csr5_auto_sigma(nRow, len(row))      # anonymouslib_cuda.h:293-317
+            want = {-1: ref_rule, 0: max(ref_rule, 16)}.get(sigma, sigma)
+            assert A_opt.scalar("sigma") == want, (name, sigma)
+            m = oracle.csr5_convert(nRow, row, col, val, want)
             check_csr5_arrays(A_opt, m, (name, sigma))
             assert_y(y, y_ref, row, col, val, x, nRow)
             assert_y(y, oracle.csr5_spmv(m, x), row, col, val, x, nRow)
