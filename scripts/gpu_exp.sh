@@ -1,6 +1,6 @@
 source scripts/gpu_check.sh exp > /dev/null 2>&1
-for u in 3 5 7 9; do
-B200SPMV_DIA_U=$u run c4_dia_u$u --workload c4 --steps 20 --no-cpu
-B200SPMV_DIA_U=$u run c5_dia_u$u --workload c5 --format dia --steps 10 --no-cpu
-B200SPMV_DIA_U=$u run c1_dia_u$u --workload c1 --format dia --steps 50 --no-cpu
-done
+for m in 0 1; do for it in 4 8 16; do
+B200SPMV_RBS_MODE=$m B200SPMV_RBS_ITERS=$it run c5_crs_m${m}_i$it --workload c5 --format crs --steps 10 --no-cpu
+done; done
+B200SPMV_RBS_MODE=0 run c1_crs_m0 --workload c1 --format crs --steps 50 --no-cpu
+B200SPMV_RBS_MODE=1 run c1_crs_m1 --workload c1 --format crs --steps 50 --no-cpu

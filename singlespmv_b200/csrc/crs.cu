@@ -1,5 +1,9 @@
 // crs.cu -- CRS plugin: device conversion + adaptive tile-stream multiply.
 // Reference: /root/reference/src/opt_crs.{h,cpp} (SpMatOpt{ptr,idx,val}; OptimizeProblem :10-42; SpMV :44-70).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -18,7 +22,69 @@ __global__ void crs_to_f64_kernel(const float *__restrict__ in, int n, double *_
     if (i < n) out[i] = (double)in[i];
 }
 
+// ---- short-row path ("row-block stream"): used when the longest row has at most RBS_MAXLEN entries.
+// A warp owns 32 consecutive rows at a time.  Their entries are one contiguous run of the idx/val streams, so the
+// warp reads them lane-contiguously (a request = 128 B of idx / 256 B of val), gathers x, parks the products in
+// its PRIVATE slice of shared memory (__syncwarp only: no block barrier, no tiles, no carries, one launch), and
+// then every lane sums its own row in ascending column order with unfused mul/add -> bit-identical to the
+// reference for every row.  The tile-stream kernel stays the path for everything with longer or skewed rows.
+constexpr int RBS_MAXLEN = 16;
+constexpr int RBS_WARPS = 8;
+constexpr int RBS_ITERS = 8;      // row blocks per warp
+
+__device__ __forceinline__ double rbs_ld(const double *p, uint64_t pol) { return ld_stream_d1(p, pol); }
+__device__ __forceinline__ double rbs_ld(const float *p, uint64_t) { return (double)__ldg(p); }
+
+template <typename VT, int U, int MINB>
+__global__ void __launch_bounds__(RBS_WARPS * 32, MINB)
+crs_rowblock_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, const VT *__restrict__ val,
+                    const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int cap, int iters)
+{
+    extern __shared__ __align__(16) double rbs_prod[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *prod = rbs_prod + (size_t)warp * cap;
+    const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
+    const long long gw = (long long)blockIdx.x * RBS_WARPS + warp;
+    // a warp walks RBS_ITERS consecutive row blocks.  Measured alternatives (profiles/r1_experiments.md): dealing the
+    // blocks round-robin to the warps of a CTA, prefetching the next block's row pointers, 16 blocks per warp and
+    // batches of 4 instead of 8 loads per lane were all slower on c5 (682-702 vs 748 GFLOP/s)
+    for (int it = 0; it < iters; it++) {
+        const long long r0l = (long long)rowBegin + (gw * iters + it) * 32;
+        if (r0l >= rowEnd) break;                                // warp-uniform
+        const int r0 = (int)r0l, r = r0 + lane;
+        const int p = ptr[min(r, rowEnd)], q = ptr[min(r + 1, rowEnd)];
+        const int base = __shfl_sync(0xffffffffu, p, 0), end = __shfl_sync(0xffffffffu, q, 31);
+        const int n = end - base;                                // <= 32 * RBS_MAXLEN <= cap
+        for (int k0 = 0; k0 < n; k0 += 32 * U) {
+            int c[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0 + u * 32 + lane;
+                if (k < n) {
+                    c[u] = ld_stream_i1(idx + base + k, pol_stream);
+                    v[u] = rbs_ld(val + base + k, pol_stream);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0 + u * 32 + lane;
+                if (k < n) prod[k] = __dmul_rn(v[u], ld_x(x + c[u], pol_x));
+            }
+        }
+        __syncwarp();
+        if (r < rowEnd) {
+            double acc = 0.0;
+            for (int j = p - base; j < q - base; j++) acc = __dadd_rn(acc, prod[j]);
+            y[r] = acc;
+        }
+        __syncwarp();
+    }
+}
+
 struct CrsFormat : Format {
+    int maxLen = 0;
+    bool short_rows = false;
     DevBuf<int> ptr, idx;
     DevBuf<double> val;
     DevBuf<float> val32;
@@ -45,13 +111,30 @@ struct CrsFormat : Format {
             B2_CUDA(cudaMemcpyAsync(val.p, A.val, val.bytes(), cudaMemcpyDeviceToDevice, s));   // :30
             B2_TRY(ts.build(ptr.p, idx.p, val.p, false, nRow, nnz, s));
         }
+        B2_TRY(max_row_length(ptr.p, nRow, &maxLen, s));
+        static const char *force = getenv("B200SPMV_CRS_PATH");                 // "tile" | "rows" (experiments)
+        short_rows = nnz > 0 && maxLen <= RBS_MAXLEN;
+        if (force && !strcmp(force, "tile")) short_rows = false;
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
-    int multiply(const double *x, double *y, cudaStream_t s) override { return ts.run_all(x, y, false, s); }
+    int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
 
-    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override { return ts.run_rows(x, y, false, rb, re, s); }
+    int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
+    {
+        if (!short_rows) return ts.run_rows(x, y, false, rb, re, s);
+        if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re) return B200SPMV_OK;
+        const int cap = 32 * ((maxLen + 1) & ~1);                               // doubles per warp, 16-byte multiple
+        const int iters = RBS_ITERS;
+        const int grid = ceil_div(re - rb, RBS_WARPS * iters * 32);
+        const size_t smem = (size_t)RBS_WARPS * cap * sizeof(double);
+        if (f32) crs_rowblock_kernel<float, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr.p, idx.p, val32.p, x, y, rb, re, cap, iters);
+        else crs_rowblock_kernel<double, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr.p, idx.p, val.p, x, y, rb, re, cap, iters);
+        B2_KERNEL_CHECK();
+        return B200SPMV_OK;
+    }
     bool has_rows() const override { return true; }
 
     bool scalar(const std::string &n, long long *out) override
@@ -60,7 +143,9 @@ struct CrsFormat : Format {
             *out = (f32 ? 8LL : 12LL) * nnz + 4LL * (nRow + 1) + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = ts.nTiles > 1 ? 2 : 1; return true; }
+        if (n == "launches") { *out = short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
+        if (n == "maxLength") { *out = maxLen; return true; }
+        if (n == "short_row_path") { *out = short_rows ? 1 : 0; return true; }
         if (n == "nTiles") { *out = ts.nTiles; return true; }
         if (n == "value_f32") { *out = f32 ? 1 : 0; return true; }
         return false;

@@ -342,7 +342,10 @@ struct DiaFormat : Format {
             B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
             return B200SPMV_OK;
         }
-        static const int du = getenv("B200SPMV_DIA_U") ? atoi(getenv("B200SPMV_DIA_U")) : DIA_U;
+        // diagonals per load round, measured (profiles/r1_experiments.md): 27 diagonals want 7 (c4: 0.99 of the copy
+        // peak, 5 gives 0.88), 7 diagonals want 3 (c5: 1.06 vs 0.99), up to 5 diagonals go in one round
+        static const int du_env = getenv("B200SPMV_DIA_U") ? atoi(getenv("B200SPMV_DIA_U")) : 0;
+        const int du = du_env ? du_env : (nDiag >= 16 ? 7 : nDiag <= 5 ? 5 : 3);
         if (tma_ok && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             const int grid = ceil_div(re - rb, DIA_R);
             if (du == 7) dia_spmv_tma_kernel<7, 5><<<grid, DIA_THREADS, smem_bytes, s>>>(diag.p, ld, nDiag, runs, x, y, rb, re, nCol);
