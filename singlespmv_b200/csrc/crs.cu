@@ -82,6 +82,27 @@ crs_rowblock_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, co
     }
 }
 
+// y[rb..re) = A x for matrices whose longest row has at most RBS_MAXLEN entries (CRS and SS share it)
+int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
+                  double *y, cudaStream_t s)
+{
+    if (rb >= re) return B200SPMV_OK;
+    const int cap = 32 * ((maxLen + 1) & ~1);                               // doubles per warp, 16-byte multiple
+    const int iters = RBS_ITERS;
+    const int grid = ceil_div(re - rb, RBS_WARPS * iters * 32);
+    const size_t smem = (size_t)RBS_WARPS * cap * sizeof(double);
+    if (f32) crs_rowblock_kernel<float, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr, idx, static_cast<const float *>(val), x, y, rb, re, cap, iters);
+    else crs_rowblock_kernel<double, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr, idx, static_cast<const double *>(val), x, y, rb, re, cap, iters);
+    B2_KERNEL_CHECK();
+    return B200SPMV_OK;
+}
+bool rowblock_applies(int maxLen, long long nnz)
+{
+    static const char *force = getenv("B200SPMV_CRS_PATH");                 // "tile" forces the tile-stream (experiments)
+    if (force && !strcmp(force, "tile")) return false;
+    return nnz > 0 && maxLen <= RBS_MAXLEN;
+}
+
 struct CrsFormat : Format {
     int maxLen = 0;
     bool short_rows = false;
@@ -112,9 +133,7 @@ struct CrsFormat : Format {
             B2_TRY(ts.build(ptr.p, idx.p, val.p, false, nRow, nnz, s));
         }
         B2_TRY(max_row_length(ptr.p, nRow, &maxLen, s));
-        static const char *force = getenv("B200SPMV_CRS_PATH");                 // "tile" | "rows" (experiments)
-        short_rows = nnz > 0 && maxLen <= RBS_MAXLEN;
-        if (force && !strcmp(force, "tile")) short_rows = false;
+        short_rows = rowblock_applies(maxLen, nnz);
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
@@ -126,14 +145,7 @@ struct CrsFormat : Format {
         if (!short_rows) return ts.run_rows(x, y, false, rb, re, s);
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
-        const int cap = 32 * ((maxLen + 1) & ~1);                               // doubles per warp, 16-byte multiple
-        const int iters = RBS_ITERS;
-        const int grid = ceil_div(re - rb, RBS_WARPS * iters * 32);
-        const size_t smem = (size_t)RBS_WARPS * cap * sizeof(double);
-        if (f32) crs_rowblock_kernel<float, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr.p, idx.p, val32.p, x, y, rb, re, cap, iters);
-        else crs_rowblock_kernel<double, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr.p, idx.p, val.p, x, y, rb, re, cap, iters);
-        B2_KERNEL_CHECK();
-        return B200SPMV_OK;
+        return rowblock_spmv(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, maxLen, rb, re, x, y, s);
     }
     bool has_rows() const override { return true; }
 

@@ -23,7 +23,7 @@ constexpr int DIA_RPT = 2;
 constexpr int DIA_R = DIA_THREADS * DIA_RPT;
 constexpr int DIA_MAX_DIAG = 64;     // TMA variant: per-diagonal window bases live in shared memory
 constexpr int DIA_MAX_RUNS = 16;
-constexpr int DIA_U = 5;            // diagonals per load round
+
 
 struct DiaRuns {
     int n;

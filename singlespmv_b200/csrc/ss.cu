@@ -223,7 +223,8 @@ static int faithful_fold(const DevBuf<int> &segs, const std::vector<int> &counts
 
 // ================================================================= SS
 struct SsFormat : Format {
-    int W, H = 0, nStep = 0, faithful;
+    int W, H = 0, nStep = 0, faithful, maxLen = 0;
+    bool short_rows = false;
     DevBuf<int> row_ptr, row2d, col2d, seg_index, segs;
     DevBuf<double> val2d, val_buf;
     std::vector<int> counts;
@@ -249,6 +250,8 @@ struct SsFormat : Format {
         }
         B2_TRY(build_chain(row2d.p, H, W, seg_index.p, &nStep, counts, segs, s));
         B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, s));
+        B2_TRY(max_row_length(row_ptr.p, nRow, &maxLen, s));
+        short_rows = rowblock_applies(maxLen, nnz);
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
@@ -256,7 +259,7 @@ struct SsFormat : Format {
 
     int multiply(const double *x, double *y, cudaStream_t s) override
     {
-        if (!faithful) return ts.run_all(x, y, false, s);
+        if (!faithful) return multiply_rows(0, nRow, x, y, s);
         if (nRow == 0) return B200SPMV_OK;
         const long long slots = (long long)H * W;
         if (slots) {
@@ -273,6 +276,10 @@ struct SsFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful) return Format::multiply_rows(rb, re, x, y, s);
+        if (short_rows) {        // same fused product+sum, warp-per-32-rows stream (crs.cu)
+            if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+            return rowblock_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, s);
+        }
         return ts.run_rows(x, y, false, rb, re, s);
     }
 
@@ -286,7 +293,7 @@ struct SsFormat : Format {
             return true;
         }
         if (n == "launches") {
-            if (!faithful) { *out = ts.nTiles > 1 ? 2 : 1; return true; }
+            if (!faithful) { *out = short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
             int l = 2;
             for (int c : counts) l += c > 0;
             *out = l;

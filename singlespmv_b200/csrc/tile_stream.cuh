@@ -62,4 +62,9 @@ struct TileStream {
     std::map<std::pair<int, int>, std::pair<int, int>> range_cache;
 };
 
+// short-row alternative to the tile-stream (crs.cu): warp-per-32-rows stream, no tiles, one launch
+int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
+                  double *y, cudaStream_t s);
+bool rowblock_applies(int maxLen, long long nnz);
+
 }  // namespace b2
