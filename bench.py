@@ -57,7 +57,7 @@ NCU_TRAFFIC = {("c2", "css", 3): 2415011680, ("c2", "ell", 0): 37576549544, ("c2
                ("c3", "crs", 0): 3308867896, ("c3", "csr5", 0): 3383375304, ("c4", "dia", 0): 3864375128,
                ("c4", "ell", 0): 5853024560, ("c5", "crs", 0): 13933793000, ("c5", "coo", 0): 17818634000,
                ("c1", "crs", 0): 77940224}
-DOMINANT = {"crs": "tile_stream_kernel", "ss": "tile_stream_kernel", "css": "tile_stream_kernel (one launch per column block)",
+DOMINANT = {"crs": "crs_rowblock_kernel (longest row <= 16) / tile_stream_kernel", "ss": "tile_stream_kernel", "css": "tile_stream_kernel (one launch per column block)",
             "ell": "ell_spmv_kernel", "jds": "jds_spmv_kernel", "dia": "dia_spmv_tma_kernel", "coo": "coo_tile_kernel",
             "csr5": "c5_compute_kernel"}
 

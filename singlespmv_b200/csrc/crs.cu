@@ -91,6 +91,10 @@ int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int
     const int iters = RBS_ITERS;
     const int grid = ceil_div(re - rb, RBS_WARPS * iters * 32);
     const size_t smem = (size_t)RBS_WARPS * cap * sizeof(double);
+    if (smem > 48 * 1024) {
+        B2_CUDA(cudaFuncSetAttribute(crs_rowblock_kernel<float, 8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CUDA(cudaFuncSetAttribute(crs_rowblock_kernel<double, 8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (f32) crs_rowblock_kernel<float, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr, idx, static_cast<const float *>(val), x, y, rb, re, cap, iters);
     else crs_rowblock_kernel<double, 8, 5><<<grid, RBS_WARPS * 32, smem, s>>>(ptr, idx, static_cast<const double *>(val), x, y, rb, re, cap, iters);
     B2_KERNEL_CHECK();
@@ -100,7 +104,8 @@ bool rowblock_applies(int maxLen, long long nnz)
 {
     static const char *force = getenv("B200SPMV_CRS_PATH");                 // "tile" forces the tile-stream (experiments)
     if (force && !strcmp(force, "tile")) return false;
-    return nnz > 0 && maxLen <= RBS_MAXLEN;
+    static const int lim = getenv("B200SPMV_RBS_MAXLEN") ? atoi(getenv("B200SPMV_RBS_MAXLEN")) : RBS_MAXLEN;
+    return nnz > 0 && maxLen <= lim;
 }
 
 struct CrsFormat : Format {

@@ -379,7 +379,7 @@ def run_partitioned_bench(args, wl, wl_key):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None,
                              "peak_source": peak_src + " x %d GPUs" % world, "alg_bytes_per_launch": alg_bytes,
-                             "kernel": "tile_stream_kernel (CRS), whole step incl. exposed halo exchange"},
+                             "kernel": "CRS multiply (crs_rowblock_kernel for short rows, else tile_stream_kernel): whole step incl. exposed halo exchange"},
                 "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
                         "h2d_bytes_per_step": 8 * nRow, "d2h_bytes_per_step": 8 * nRow},
                 "gpu_launches": int(launches.item()) * args.steps, "clocks": clocks}
