@@ -71,7 +71,9 @@ typedef struct {
                             operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
     int value_f32;       /* CRS: 1 = store the matrix values as fp32 (rounded once at conversion); x, y and all
                             arithmetic stay fp64.  8 instead of 12 B/nnz; tolerance 1e-5 (BASELINE.json north star) */
-    int reserved[11];
+    int crs_path;        /* CRS / SS: 0 = choose from the longest row, 1 = always the tile-stream kernel,
+                            2 = row-block stream whenever it applies (longest row <= 16) */
+    int reserved[10];
 } b200spmv_options;
 
 /* ---- library ---- */

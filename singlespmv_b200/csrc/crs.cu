@@ -116,7 +116,8 @@ struct CrsFormat : Format {
     DevBuf<float> val32;
     bool f32;
     TileStream ts;
-    explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0) {}
+    int path_opt;
+    explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0), path_opt(o.crs_path) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -138,7 +139,7 @@ struct CrsFormat : Format {
             B2_TRY(ts.build(ptr.p, idx.p, val.p, false, nRow, nnz, s));
         }
         B2_TRY(max_row_length(ptr.p, nRow, &maxLen, s));
-        short_rows = rowblock_applies(maxLen, nnz);
+        short_rows = path_opt != 1 && rowblock_applies(maxLen, nnz);
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }

@@ -230,7 +230,8 @@ struct SsFormat : Format {
     std::vector<int> counts;
     TileStream ts;
 
-    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful) {}
+    int path_opt;
+    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful), path_opt(o.crs_path) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -251,7 +252,7 @@ struct SsFormat : Format {
         B2_TRY(build_chain(row2d.p, H, W, seg_index.p, &nStep, counts, segs, s));
         B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, s));
         B2_TRY(max_row_length(row_ptr.p, nRow, &maxLen, s));
-        short_rows = rowblock_applies(maxLen, nnz);
+        short_rows = path_opt != 1 && rowblock_applies(maxLen, nnz);
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;

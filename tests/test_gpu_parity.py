@@ -158,6 +158,26 @@ def test_host_multiply_pipeline_large(sp, oracle, fmt, opt):
             assert np.array_equal(y2, y2_ref)
 
 
+def test_crs_paths_agree(sp, oracle):
+    """Short-row matrices take the row-block stream by default; crs_path=1 forces the tile-stream.  Both sum every
+    row in the reference's order -> identical y, and both equal the reference CRS result bit for bit."""
+    for kind, n in (("lap3d7", 21), ("lap2d5", 130)):
+        nr, nc, row, col, val = oracle.stencil(kind, n)
+        x = oracle.reference_vectors(nc, nr)[0]
+        y_ref = oracle.crs_result(nr, row, col, val, x)
+        for fmt in ("crs", "ss"):
+            A_auto, y_auto = run_host(sp, fmt, nr, nc, row, col, val, x)
+            A_tile, y_tile = run_host(sp, fmt, nr, nc, row, col, val, x, crs_path=1)
+            if fmt == "crs":
+                assert A_auto.scalar("short_row_path") == 1 and A_tile.scalar("short_row_path") == 0
+                assert A_auto.scalar("launches") == 1 and A_tile.scalar("launches") == 2
+            assert np.array_equal(y_auto, y_ref) and np.array_equal(y_tile, y_ref)
+    # longer rows: the row-block stream does not apply
+    nr, nc, row, col, val = oracle.stencil("box3d27", 9)
+    A_opt, _ = run_host(sp, "crs", nr, nc, row, col, val, np.ones(nc))
+    assert A_opt.scalar("short_row_path") == 0 and A_opt.scalar("maxLength") == 27
+
+
 def test_crs_f32_storage(sp, oracle, all_cases):
     """options.value_f32: values rounded to fp32 once, arithmetic in fp64.  Two checks: (1) bit-identical to the
     fp64 path run on the rounded matrix (fp32 -> fp64 widening is exact), (2) within the north star's 1e-5 of the
