@@ -54,8 +54,9 @@ MINI = {"c1": dict(p0=128), "c2": dict(p0=1 << 16), "c3": dict(p0=14, p1=1 << 18
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # captures (profiles/r1_ncu_kernels.md).  Keyed by (workload, format, n_block); anything else reports null.
 NCU_TRAFFIC = {("c2", "css", 3): 2415011680, ("c2", "ell", 0): 37576549544, ("c2", "jds", 0): 33652983616,
-               ("c3", "crs", 0): 3308867896, ("c3", "csr5", 0): 3383375304, ("c4", "dia", 0): 3864375128,
-               ("c4", "ell", 0): 5853024560, ("c5", "coo", 0): 17818634000}
+               ("c3", "crs", 0): 3308867896, ("c3", "csr5", 0): 3383375304, ("c4", "dia", 0): 3870562096,
+               ("c4", "ell", 0): 5853024560, ("c5", "crs", 0): 14787440000, ("c5", "dia", 0): 9634725000,
+               ("c5", "csr5", 0): 13638726000, ("c5", "coo", 0): 20025184000}
 DOMINANT = {"crs": "crs_rowblock_kernel (longest row <= 16) / tile_stream_kernel", "ss": "tile_stream_kernel", "css": "tile_stream_kernel (one launch per column block)",
             "ell": "ell_spmv_kernel", "jds": "jds_spmv_kernel", "dia": "dia_spmv_tma_kernel", "coo": "coo_tile_kernel",
             "csr5": "c5_compute_kernel"}
