@@ -13,7 +13,6 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
 from ._lib import FORMATS, SYNTH, B200SpmvError, Coo, Options, Stats, check, lib
 
 
