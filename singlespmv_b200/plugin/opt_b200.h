@@ -15,7 +15,8 @@
 // Inside the reference tree: add `#elif defined(OPT_B200) / #include "opt_b200.h"` to src/opt.h and the
 // matching `#include "opt_b200.cpp"` to src/opt.cpp (README.md:5-8 procedure); see INTEGRATION.md.
 #pragma once
-#include "util.h"            // SpMat, Vec: the reference's src/util.h:7-28, or plugin/util.h (same layout) standalone
+#include "util.h"            // SpMat, Vec: the host project's util.h -- the reference's src/util.h:7-28 inside its tree,
+                             // plugin/standalone/util.h (same names and layout) for the driver built here
 #include "b200spmv.h"
 
 struct SpMatOpt {

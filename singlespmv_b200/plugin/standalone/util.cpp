@@ -1,4 +1,4 @@
-// util.cpp -- the driver-side helpers of plugin/util.h, restated from the behaviour of the reference's
+// util.cpp -- the driver-side helpers of plugin/standalone/util.h, restated from the behaviour of the reference's
 // src/util.cpp (loader: first line not starting with '%' is "M N L", then exactly L "row col val"
 // triples, 1-based, sorted by (row, col), duplicates kept, banner/symmetry ignored).
 #include "util.h"

@@ -53,9 +53,10 @@ def build(prefix, option, bin_dir, cuda="/usr/local/cuda"):
     os.makedirs(bin_dir, exist_ok=True)
     exe = os.path.join(bin_dir, "%s-spmv.gpu" % prefix)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-std=c++11", "-O2", "-DGPU", "-I" + PLUGIN, "-I" + os.path.join(ROOT, "include"), "-I" + cuda + "/include"]
+    cmd = [cxx, "-std=c++11", "-O2", "-DGPU", "-I" + PLUGIN, "-I" + os.path.join(PLUGIN, "standalone"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + cuda + "/include"]
     cmd += shlex.split(option)
-    cmd += [os.path.join(PLUGIN, f) for f in ("main_b200.cpp", "opt_b200.cpp", "util.cpp")]
+    cmd += [os.path.join(PLUGIN, f) for f in ("main_b200.cpp", "opt_b200.cpp", os.path.join("standalone", "util.cpp"))]
     cmd += ["-o", exe, "-L" + PKG, "-lb200spmv", "-L" + cuda + "/lib64", "-lcudart", "-Wl,-rpath," + PKG,
             "-Wl,-rpath," + cuda + "/lib64"]
     subprocess.check_call(cmd)
