@@ -1,4 +1,4 @@
-// crs.cu -- CRS plugin: device conversion + adaptive tile-stream multiply.
+// crs.cu -- CRS plugin: device conversion + adaptive multiply (row-block stream for short rows, tile-stream otherwise).
 // Reference: /root/reference/src/opt_crs.{h,cpp} (SpMatOpt{ptr,idx,val}; OptimizeProblem :10-42; SpMV :44-70).
 #include <algorithm>
 #include <cstdlib>
