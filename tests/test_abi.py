@@ -85,3 +85,37 @@ def test_reference_vectors_match_the_oracle(oracle):
     xo, yo = oracle.reference_vectors(17, 9, 3)
     assert np.array_equal(x, xo) and np.array_equal(y, yo)
     assert x[0] == 0.56138017520372763
+
+
+def test_recommend_format_rules_on_cpu():
+    """b200spmv_recommend_format is pure host logic: the rule table on the BASELINE.json shapes from their closed-form
+    statistics (the device side, b200spmv_analyze, is checked in tests/test_gpu_parity.py)."""
+    import singlespmv_b200 as sp
+    from singlespmv_b200._lib import Options, Stats, lib
+
+    def rec(**kw):
+        st = Stats()
+        for k, v in kw.items():
+            setattr(st, k, v)
+        o = Options()
+        f = lib.b200spmv_recommend_format(C.byref(st), C.byref(o))
+        return [k for k, v in sp.FORMATS.items() if v == f][0], o.n_block
+    n2 = 1 << 24
+    assert rec(nRow=1 << 20, nCol=1 << 20, nnz=5238784, rowMax=5, rowMean=4.996, rowVar=0.004, nDiag=5)[0] == "dia"              # c1
+    assert rec(nRow=n2, nCol=n2, nnz=n2 * 32, rowMax=32, rowMin=32, rowMean=32.0, rowVar=0.0, nDiag=2 * n2 - 1) == ("css", 3)   # c2
+    assert rec(nRow=1 << 23, nCol=1 << 23, nnz=258673573, rowMax=400000, rowMean=30.8, rowVar=1e5, nDiag=1 << 24)[0] == "csr5"  # c3
+    assert rec(nRow=256 ** 3, nCol=256 ** 3, nnz=766 ** 3, rowMax=27, rowMean=26.8, rowVar=0.5, nDiag=27)[0] == "dia"           # c4
+    assert rec(nRow=512 ** 3, nCol=512 ** 3, nnz=937951232, rowMax=7, rowMean=6.99, rowVar=0.01, nDiag=7)[0] == "dia"           # c5
+    assert rec(nRow=1 << 16, nCol=1 << 16, nnz=32 << 16, rowMax=32, rowMean=32.0, rowVar=0.0, nDiag=100000)[0] == "ell"
+    assert rec(nRow=1000, nCol=1000, nnz=9000, rowMax=40, rowMean=9.0, rowVar=20.0, nDiag=900)[0] == "crs"
+    assert rec(nRow=10, nCol=10, nnz=0)[0] == "crs"
+
+
+def test_baseline_shapes_closed_form(oracle):
+    """The synthetic generators' sizes are the ones BASELINE.json / SURVEY.md 8 quote."""
+    L = oracle.lib
+    assert (L.synth_stencil_rows(0, 1024), L.synth_stencil_nnz(0, 1024)) == (1048576, 5238784)          # c1
+    assert (L.synth_stencil_rows(2, 256), L.synth_stencil_nnz(2, 256)) == (16777216, 766 ** 3)          # c4
+    assert (L.synth_stencil_rows(1, 512), L.synth_stencil_nnz(1, 512)) == (134217728, 937951232)        # c5
+    for kind, n in ((0, 7), (1, 5), (2, 4)):                                                            # closed form == generator
+        assert L.synth_stencil_nnz(kind, n) == len(oracle.stencil({0: "lap2d5", 1: "lap3d7", 2: "box3d27"}[kind], n)[2])
