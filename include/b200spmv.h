@@ -18,7 +18,10 @@
  *   - input is COO sorted by (row, col) without duplicate coordinates (src/util.cpp:51)
  *   - every function returns 0 on success or a negative b200spmv_status; it never exits
  *     (the reference's plugins assert()/exit(): src/util.h:48-55, src/util.cpp:32-35)
- *   - a handle is used from one host thread at a time
+ *   - a handle is used from one host thread at a time, and its multiplies are serialised on ONE stream at a time:
+ *     rows that cross tile boundaries are finished through per-handle carry buffers, so two multiplies of the same
+ *     handle in flight on different streams would race (b200spmv_multiply_host uses its own private streams: do not
+ *     overlap it with b200spmv_multiply on the same handle)
  *   - there is NO CPU fallback: without a CUDA device every compute entry fails with
  *     B200SPMV_ERR_CUDA.
  */
@@ -73,7 +76,10 @@ typedef struct {
                             arithmetic stay fp64.  8 instead of 12 B/nnz; tolerance 1e-5 (BASELINE.json north star) */
     int crs_path;        /* CRS / SS: 0 = choose from the longest row, 1 = always the tile-stream kernel,
                             2 = row-block stream whenever it applies (longest row <= 16) */
-    int reserved[10];
+    int profile;         /* SS/CSS with ss_faithful: time the Mul and the Sum phase of every multiply with CUDA events
+                            (the reference's -DPROFILING, src/util.h:59-65); the multiply then synchronises and the
+                            scalars MulTime_ns / SumTime_ns hold the last call's phases */
+    int reserved[9];
 } b200spmv_options;
 
 /* ---- library ---- */
@@ -110,6 +116,21 @@ B200SPMV_API int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, d
  * b200spmv_multiply_host to overlap the D2H copy of finished rows with the rest of the multiply. */
 B200SPMV_API int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const double *x_d,
                            double *y_d, void *stream);
+
+/* Host-side bookkeeping for a row range (reads two row pointers back: synchronises).  multiply_rows on a prepared
+ * range never synchronises and can be captured in a CUDA graph; an unprepared range is prepared on first use
+ * (refused with B200SPMV_ERR_STATE inside a stream capture). */
+B200SPMV_API int b200spmv_prepare_rows(b200spmv_matrix *m, int rowBegin, int rowEnd);
+/* Smallest and largest column referenced by rows [rowBegin,rowEnd) (conservative: CRS, SS, ELL, DIA look at their
+ * arrays, the other formats answer [0, nCol-1]; colMax < colMin = the rows are empty).  Lets a caller that streams x
+ * in from the host (or from a peer GPU) start a row range as soon as that part of x is there. */
+B200SPMV_API int b200spmv_rows_col_extent(b200spmv_matrix *m, int rowBegin, int rowEnd, int *colMin, int *colMax);
+/* Page-lock / release a caller-owned host vector.  b200spmv_multiply_host overlaps H2D x, the multiply and D2H y
+ * only when BOTH vectors are page-locked; with pageable vectors (the reference's _mm_malloc'ed x and y,
+ * src/util.cpp:92-102) it falls back to copy - multiply - copy.  The plugin layer registers x in OptimizeProblem
+ * and y on the first SpMV; the caller must keep a registered range alive until it is unregistered. */
+B200SPMV_API int b200spmv_host_register(void *p, unsigned long long bytes);
+B200SPMV_API int b200spmv_host_unregister(void *p);
 
 /* ---- read-back for parity checks: the SpMatOpt fields under the reference's names.
  * Scalars: nRow nCol nNnz | K | maxLength | nDiag | H nStep W | B nBlock totalH | sigma p ... and

@@ -5,4 +5,4 @@ this package is the thin host-side mirror of the reference's OptimizeProblem / S
 """
 from ._lib import LIB_PATH, B200SpmvError, FORMATS, SYNTH          # noqa: F401
 from .plugin import (DeviceCoo, OptimizeProblem, SpMat, SpMatOpt, SpMV, Vec, VecOpt,   # noqa: F401
-                     device_count, reference_vectors)
+                     device_count, host_register, host_unregister, reference_vectors)

@@ -21,7 +21,7 @@ class B200SpmvError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("segment_width", C.c_int), ("n_block", C.c_int), ("csr5_sigma", C.c_int),
-                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("reserved", C.c_int * 10)]
+                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("reserved", C.c_int * 9)]
 
 
 class Stats(C.Structure):
@@ -54,6 +54,10 @@ def _load():
     lib.b200spmv_multiply.argtypes = [vp, vp, vp, vp]
     lib.b200spmv_multiply_host.argtypes = [vp, vp, vp]
     lib.b200spmv_multiply_rows.argtypes = [vp, ip, ip, vp, vp, vp]
+    lib.b200spmv_prepare_rows.argtypes = [vp, ip, ip]
+    lib.b200spmv_rows_col_extent.argtypes = [vp, ip, ip, C.POINTER(ip), C.POINTER(ip)]
+    lib.b200spmv_host_register.argtypes = [vp, C.c_ulonglong]
+    lib.b200spmv_host_unregister.argtypes = [vp]
     lib.b200spmv_get_scalar.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
     lib.b200spmv_get_array.argtypes = [vp, C.c_char_p, vp, ll]
     lib.b200spmv_get_array.restype = ll

@@ -16,7 +16,7 @@ int b2::xload_mode()
     return m;
 }
 
-constexpr int B200SPMV_HOST_CHUNKS = 8;
+constexpr int B200SPMV_HOST_CHUNKS = 32;
 constexpr int B200SPMV_HOST_SLICES = 64;
 
 struct b200spmv_matrix {
@@ -24,6 +24,10 @@ struct b200spmv_matrix {
     b200spmv_options opt{};
     std::unique_ptr<Format> impl;
     bool converted = false;
+    // plan of the host-semantics pipeline (built on first use)
+    int plan_chunks = 0, plan_pieces = 0;
+    int chunk_rb[B200SPMV_HOST_CHUNKS + 1] = {}, chunk_need[B200SPMV_HOST_CHUNKS] = {};
+    long long piece_c0[B200SPMV_HOST_SLICES + 1] = {};
     // staging for host-semantics multiply
     DevBuf<double> x_stage, y_stage;
     cudaStream_t stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
@@ -152,6 +156,7 @@ int b200spmv_convert_coo_device(b200spmv_matrix *m, int nRow, int nCol, long lon
     B2_TRY(require_device());
     CooView A{nRow, nCol, (int)nnz, row_d, col_d, val_d};
     m->converted = false;
+    m->plan_chunks = m->plan_pieces = 0;
     int st = m->impl->convert(A, (cudaStream_t)stream);
     if (st == B200SPMV_OK) m->converted = true;
     return st;
@@ -206,6 +211,81 @@ int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const d
     return m->impl->multiply_rows(rowBegin, rowEnd, x_d, y_d, (cudaStream_t)stream);
 }
 
+int b200spmv_prepare_rows(b200spmv_matrix *m, int rowBegin, int rowEnd)
+{
+    clear_error();
+    if (!m) { set_error("prepare_rows: NULL handle"); return B200SPMV_ERR_INVALID; }
+    if (!m->converted) { set_error("prepare_rows: matrix not converted yet"); return B200SPMV_ERR_STATE; }
+    return m->impl->prepare_rows(rowBegin, rowEnd);
+}
+
+int b200spmv_rows_col_extent(b200spmv_matrix *m, int rowBegin, int rowEnd, int *colMin, int *colMax)
+{
+    clear_error();
+    if (!m || !colMin || !colMax) { set_error("rows_col_extent: NULL argument"); return B200SPMV_ERR_INVALID; }
+    if (!m->converted) { set_error("rows_col_extent: matrix not converted yet"); return B200SPMV_ERR_STATE; }
+    return m->impl->col_extent(rowBegin, rowEnd, colMin, colMax);
+}
+
+// Page-locks a caller-owned host range so that copies to and from it are true asynchronous DMA (the reference's
+// driver allocates x and y with _mm_malloc: pageable).  Already pinned memory is accepted as is.
+int b200spmv_host_register(void *p, unsigned long long bytes)
+{
+    clear_error();
+    if (!p || bytes == 0) { set_error("host_register: empty range"); return B200SPMV_ERR_INVALID; }
+    B2_TRY(require_device());
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost) return B200SPMV_OK;
+    cudaGetLastError();
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("host_register(%p, %llu bytes): %s", p, bytes, cudaGetErrorString(e));
+        return B200SPMV_ERR_CUDA;
+    }
+    return B200SPMV_OK;
+}
+
+int b200spmv_host_unregister(void *p)
+{
+    clear_error();
+    if (!p) return B200SPMV_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("host_unregister(%p): %s", p, cudaGetErrorString(e));
+        return B200SPMV_ERR_CUDA;
+    }
+    return B200SPMV_OK;
+}
+
+static bool host_pinned(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// builds (once per handle and shape) the plan of the host-semantics pipeline: row chunks, the x piece each needs
+static int plan_host_pipeline(b200spmv_matrix *m, int nChunks, int nPieces)
+{
+    Format *f = m->impl.get();
+    if (m->plan_chunks == nChunks && m->plan_pieces == nPieces) return B200SPMV_OK;
+    const long long pieceLen = ((((long long)f->nCol + nPieces - 1) / nPieces) + 31) & ~31LL;     // 256-byte multiples
+    for (int p = 0; p <= nPieces; p++) m->piece_c0[p] = std::min<long long>(f->nCol, pieceLen * p);
+    for (int c = 0; c <= nChunks; c++)
+        m->chunk_rb[c] = c == nChunks ? f->nRow : (int)((long long)f->nRow * c / nChunks) & ~31;
+    for (int c = 0; c < nChunks; c++) {
+        B2_TRY(f->prepare_rows(m->chunk_rb[c], m->chunk_rb[c + 1]));
+        int cmin = 0, cmax = f->nCol - 1;
+        if (nPieces > 1) B2_TRY(f->col_extent(m->chunk_rb[c], m->chunk_rb[c + 1], &cmin, &cmax));
+        m->chunk_need[c] = cmax < 0 ? -1 : (int)std::min<long long>(nPieces - 1, cmax / std::max<long long>(pieceLen, 1));
+    }
+    m->plan_chunks = nChunks;
+    m->plan_pieces = nPieces;
+    return B200SPMV_OK;
+}
+
 int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
 {
     B2_TRY(check_ready(m, x_h, y_h));
@@ -219,52 +299,60 @@ int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h)
     }
     if (m->x_stage.n != (size_t)f->nCol) B2_TRY(m->x_stage.alloc((size_t)f->nCol));
     if (m->y_stage.n != (size_t)f->nRow) B2_TRY(m->y_stage.alloc((size_t)f->nRow));
-    // The reference's cuSPARSE plugin serialises H2D x, multiply, D2H y (src/opt_cusparse.cpp:72-82).  Here the
-    // three overlap where the format allows it: x goes up in the column slices the format consumes one after the
-    // other (CSS: one per column block), rows are multiplied in chunks, and the D2H copy of a finished chunk of y
-    // runs under the next chunk's multiply (PCIe is full duplex: separate in / out streams).
-    static const int env_chunks = getenv("B200SPMV_HOST_CHUNKS") ? atoi(getenv("B200SPMV_HOST_CHUNKS")) : B200SPMV_HOST_CHUNKS;
+    // The reference's cuSPARSE plugin serialises H2D x, multiply, D2H y (src/opt_cusparse.cpp:72-82).  Here the three
+    // overlap where the format and the host memory allow it:
+    //   * x goes up in pieces on its own stream (CSS: the column slices the format consumes one after the other;
+    //     everything else: ascending pieces, and a row chunk starts as soon as the pieces up to its largest column
+    //     have landed -- a banded matrix multiplies while most of x is still crossing PCIe),
+    //   * rows are multiplied in chunks, and the D2H copy of a finished chunk of y runs under the next chunk's
+    //     multiply on a third stream (PCIe is full duplex).
+    // The pipeline needs true asynchronous copies: with pageable vectors every cudaMemcpyAsync is staged and the D2H
+    // blocks the host, so the chunks would only add launches -> one H2D, one multiply, one D2H instead.
+    static const int env_chunks = getenv("B200SPMV_HOST_CHUNKS") ? atoi(getenv("B200SPMV_HOST_CHUNKS")) : 0;
+    static const int env_pieces = getenv("B200SPMV_HOST_PIECES") ? atoi(getenv("B200SPMV_HOST_PIECES")) : 0;
     static const int env_slices = getenv("B200SPMV_HOST_SLICES") ? atoi(getenv("B200SPMV_HOST_SLICES")) : 1;
-    const bool big = f->nRow >= (1 << 20);
-    const int nSlices = (env_slices && big && f->has_rows() && f->n_x_slices() <= B200SPMV_HOST_SLICES) ? f->n_x_slices() : 1;
-    // measured on c2 (profiles/r1_experiments.md): formats that stream all of x per pass gain from 8 row chunks;
-    // CSS pays for every chunk with another round of x-slice switches in L2 and is best with 2
-    int nChunks = (big && f->has_rows()) ? std::max(1, std::min(env_chunks, B200SPMV_HOST_CHUNKS)) : 1;
-    if (nSlices > 1 && !getenv("B200SPMV_HOST_CHUNKS")) nChunks = 2;
-    if (nSlices == 1) {
+    const bool big = f->nRow >= (1 << 20) && f->has_rows() && host_pinned(x_h) && host_pinned(y_h);
+    if (!big) {
         B2_CUDA(cudaMemcpyAsync(m->x_stage.p, x_h, sizeof(double) * (size_t)f->nCol, cudaMemcpyHostToDevice, m->stream));
-    } else {
-        for (int i = 0; i < nSlices; i++) {
-            long long c0, c1;
-            f->x_slice(i, &c0, &c1);
-            if (c1 > c0)
-                B2_CUDA(cudaMemcpyAsync(m->x_stage.p + c0, x_h + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, m->in_stream));
-            B2_CUDA(cudaEventRecord(m->slice_in[i], m->in_stream));
-        }
-    }
-    if (nChunks == 1 && nSlices == 1) {
         B2_TRY(f->multiply(m->x_stage.p, m->y_stage.p, m->stream));
         B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage.p, sizeof(double) * (size_t)f->nRow, cudaMemcpyDeviceToHost, m->stream));
         B2_CUDA(cudaStreamSynchronize(m->stream));
         return B200SPMV_OK;
     }
+    const bool sliced = env_slices && f->n_x_slices() > 1 && f->n_x_slices() <= B200SPMV_HOST_SLICES;   // CSS
+    // chunks of at least 4 MB of y; measured on c2 (profiles/r1_experiments.md): CSS pays for every chunk with another
+    // round of x-slice switches in L2 and is best with 2
+    const int byBytes = (int)std::max<long long>(2, std::min<long long>(16, (long long)f->nRow * 8 / (4 << 20)));
+    const int nChunks = std::max(1, std::min(env_chunks > 0 ? env_chunks : (sliced ? 2 : byBytes), B200SPMV_HOST_CHUNKS));
+    const int nPieces = sliced ? f->n_x_slices()
+                               : std::max(1, std::min(env_pieces > 0 ? env_pieces : nChunks, B200SPMV_HOST_SLICES));
+    B2_TRY(plan_host_pipeline(m, nChunks, sliced ? 1 : nPieces));
+    for (int i = 0; i < nPieces; i++) {
+        long long c0 = m->piece_c0[i], c1 = m->piece_c0[i + 1];
+        if (sliced) f->x_slice(i, &c0, &c1);
+        if (c1 > c0)
+            B2_CUDA(cudaMemcpyAsync(m->x_stage.p + c0, x_h + c0, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyHostToDevice, m->in_stream));
+        B2_CUDA(cudaEventRecord(m->slice_in[i], m->in_stream));
+    }
     for (int c = 0; c < nChunks; c++) {
-        const int rb = (int)((long long)f->nRow * c / nChunks) & ~31;
-        const int re = c + 1 == nChunks ? f->nRow : (int)((long long)f->nRow * (c + 1) / nChunks) & ~31;
-        if (nSlices == 1) {
+        const int rb = m->chunk_rb[c], re = m->chunk_rb[c + 1];
+        if (!sliced) {
+            if (m->chunk_need[c] >= 0) B2_CUDA(cudaStreamWaitEvent(m->stream, m->slice_in[m->chunk_need[c]], 0));
             B2_TRY(f->multiply_rows(rb, re, m->x_stage.p, m->y_stage.p, m->stream));
         } else {
-            for (int i = 0; i < nSlices; i++) {
+            for (int i = 0; i < nPieces; i++) {
                 if (c == 0) B2_CUDA(cudaStreamWaitEvent(m->stream, m->slice_in[i], 0));
                 B2_TRY(f->multiply_rows_slice(i, rb, re, m->x_stage.p, m->y_stage.p, m->stream));
             }
         }
         B2_CUDA(cudaEventRecord(m->chunk_done[c], m->stream));
         B2_CUDA(cudaStreamWaitEvent(m->copy_stream, m->chunk_done[c], 0));
-        B2_CUDA(cudaMemcpyAsync(y_h + rb, m->y_stage.p + rb, sizeof(double) * (size_t)(re - rb), cudaMemcpyDeviceToHost, m->copy_stream));
+        if (re > rb)
+            B2_CUDA(cudaMemcpyAsync(y_h + rb, m->y_stage.p + rb, sizeof(double) * (size_t)(re - rb), cudaMemcpyDeviceToHost, m->copy_stream));
     }
     B2_CUDA(cudaStreamSynchronize(m->copy_stream));
     B2_CUDA(cudaStreamSynchronize(m->stream));
+    B2_CUDA(cudaStreamSynchronize(m->in_stream));
     return B200SPMV_OK;
 }
 

@@ -87,6 +87,12 @@ struct Format {
         set_error("multiply_rows: this format does not support row ranges (CRS, SS, CSS, ELL, DIA do)");
         return B200SPMV_ERR_UNSUPPORTED;
     }
+    // host-side bookkeeping for a row range (may synchronise): afterwards multiply_rows on it never does
+    virtual int prepare_rows(int, int) { return B200SPMV_OK; }
+    // smallest / largest column referenced by rows [rb, re) (conservative; may synchronise).  The host-semantics
+    // pipeline uploads x in ascending pieces and starts a row chunk as soon as the pieces up to its largest column
+    // have landed: banded matrices (stencils) multiply while most of x is still crossing PCIe.
+    virtual int col_extent(int, int, int *cmin, int *cmax) { *cmin = 0; *cmax = nCol - 1; return B200SPMV_OK; }
     virtual bool has_rows() const { return false; }      // multiply_rows available (host-semantics pipeline uses it)
     // Column slices of x in order of first use (CSS: one per column block; everything else: all of x at once).
     // multiply_rows_slice(i, ...) adds slice i's contribution to rows [rb, re) (slice 0 overwrites), so the host
@@ -121,6 +127,9 @@ int max_row_length(const int *ptr_d, int nRow, int *out_h, cudaStream_t s);
 // exclusive prefix sums (CUB); out may alias in; n >= 0
 int exclusive_scan_i32(const int *in_d, int *out_d, int n, cudaStream_t s);
 int exclusive_scan_i64(const long long *in_d, long long *out_d, int n, cudaStream_t s);
+int sum_i32_as_i64(const int *in_d, int n, long long *out_h, cudaStream_t s);
+// min and max of in_d[b..e) (e > b); synchronous
+int minmax_i32(const int *in_d, long long b, long long e, int *mn_h, int *mx_h);
 // checks the input contract: sorted by (row, col), no duplicates, indices in range
 int validate_sorted_coo(const CooView &A, cudaStream_t s);
 
@@ -196,6 +205,36 @@ template <int XM> __device__ __forceinline__ double ld_x_mode(const double *p, u
     else asm volatile("ld.global.L1::evict_last.f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
+// ---------------------------------------------------------------- mbarrier / TMA (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar,
+                                            uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                 "[%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 int xload_mode();   // value of B200SPMV_XLOAD (api.cu)
 __device__ __forceinline__ double warp_sum(double v)
 {

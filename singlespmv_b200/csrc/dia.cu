@@ -12,6 +12,7 @@
 // 1-D TMA bulk copy (cp.async.bulk + mbarrier transaction count), so a 27-point stencil pulls 9
 // windows from L2 instead of 27.  Per row the diagonals are accumulated in ascending order with
 // unfused mul/add = the reference's order (and, padding zeros aside, opt_crs.cpp's) -> bit-identical y.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -65,36 +66,6 @@ __global__ void dia_logical_kernel(const double *__restrict__ diag, size_t ld, c
     const int p = (int)(i / nCol), c = (int)(i % nCol);
     const int r = c + (nRow - 1) - ioff[p];
     out[i] = (r >= 0 && r < nRow) ? diag[(size_t)p * ld + r] : 0.0;
-}
-
-// ---------------------------------------------------------------- mbarrier / TMA (sm_90+ PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// 1-D bulk copy global -> shared through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar,
-                                            uint64_t pol)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-                 "[%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 
 // window of run g for the CTA starting at row0: columns [c_lo, c_hi), smem index = col - w0
@@ -257,6 +228,7 @@ struct DiaFormat : Format {
     DevBuf<int> ioff;
     DevBuf<double> diag;
     DiaRuns runs{};
+    int offMin = 0, offMax = 0;           // smallest / largest col - row over the stored diagonals
     bool tma_ok = false;
     size_t smem_bytes = 0;
 
@@ -300,6 +272,8 @@ struct DiaFormat : Format {
         std::vector<int> h((size_t)nDiag);
         B2_CUDA(cudaStreamSynchronize(s));
         if (nDiag) B2_CUDA(cudaMemcpy(h.data(), ioff.p, sizeof(int) * (size_t)nDiag, cudaMemcpyDeviceToHost));
+        offMin = nDiag ? h[0] - shift : 0;
+        offMax = nDiag ? h[(size_t)nDiag - 1] - shift : 0;
         memset(&runs, 0, sizeof runs);
         tma_ok = nDiag > 0 && nDiag <= DIA_MAX_DIAG;
         int soff = 0;
@@ -333,6 +307,14 @@ struct DiaFormat : Format {
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
     bool has_rows() const override { return true; }
+    int col_extent(int rb, int re, int *cmin, int *cmax) override
+    {
+        if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re || nDiag == 0) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
+        *cmin = std::max(0, rb + offMin);
+        *cmax = std::min(nCol - 1, re - 1 + offMax);
+        return B200SPMV_OK;
+    }
 
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {

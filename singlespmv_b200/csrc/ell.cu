@@ -25,7 +25,7 @@ __global__ void ell_slice_groups_kernel(const int *__restrict__ ptr, int nRow, i
 template <int V>
 __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
                                 const double *__restrict__ val, int nRow, int nSlices,
-                                const long long *__restrict__ slice_off, int *__restrict__ ecol,
+                                const long long *__restrict__ slice_off, int K, int *__restrict__ ecol,
                                 double *__restrict__ eval)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -40,7 +40,9 @@ __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restri
             const int k = (int)(g - g0) * V + j;
             const size_t at = ((size_t)g * 32 + lane) * V + j;
             const bool real = k < len;
-            ecol[at] = real ? col[b + k] : (r < nRow ? k : 0);   // padding: col = slot index (opt_ell.cpp:48)
+            // padding: col = slot index (opt_ell.cpp:48) for the reference's K slots; the extra slots that round a
+            // slice up to V (k >= K, never exported) point at column 0 so that no gather leaves x when K is close to nCol
+            ecol[at] = real ? col[b + k] : ((r < nRow && k < K) ? k : 0);
             eval[at] = real ? val[b + k] : 0.0;
         }
 }
@@ -152,7 +154,7 @@ struct EllFormat : Format {
         B2_TRY(eval.alloc((size_t)slots));
         if (nSlices) {
             ell_fill_kernel<VV><<<ceil_div((long long)nSlices * 32, 256), 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices,
-                                                                                      slice_off.p, ecol.p, eval.p);
+                                                                                      slice_off.p, K, ecol.p, eval.p);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -180,6 +182,16 @@ struct EllFormat : Format {
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
     bool has_rows() const override { return true; }
+    int col_extent(int rb, int re, int *cmin, int *cmax) override
+    {
+        if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (rb == re) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
+        long long g[2] = {0, 0};                        // whole slices: padding columns (slot numbers) included
+        B2_CUDA(cudaMemcpy(&g[0], slice_off.p + rb / 32, sizeof(long long), cudaMemcpyDeviceToHost));
+        B2_CUDA(cudaMemcpy(&g[1], slice_off.p + ceil_div(re, 32), sizeof(long long), cudaMemcpyDeviceToHost));
+        if (g[1] <= g[0]) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
+        return minmax_i32(ecol.p, g[0] * 32 * V, g[1] * 32 * V, cmin, cmax);
+    }
 
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {

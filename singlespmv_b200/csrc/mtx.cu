@@ -9,6 +9,7 @@
 //   B200SPMV_MTX_REFERENCE the reference loader's semantics, bit for bit (duplicates kept, banner ignored)
 // Parsing is host work (text); sorting, mirroring bookkeeping and duplicate reduction run on the device.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <cerrno>
 #include <cstdlib>
@@ -26,6 +27,27 @@ __global__ void mtx_unpack_kernel(const unsigned long long *__restrict__ key, lo
     if (i >= n) return;
     row[i] = (int)(key[i] >> 32);
     col[i] = (int)(key[i] & 0xFFFFFFFFull);
+}
+
+// duplicate coordinates: head[i] = 1 where a run of equal keys starts (keys are sorted, stable -> file order inside a run)
+__global__ void mtx_head_kernel(const unsigned long long *__restrict__ key, long long n, char *__restrict__ head)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+// one thread per run: its entries are added left to right, i.e. in file order -- the same sum a host loop over the
+// file would produce (cub::DeviceReduce::ReduceByKey promises no order for a non-associative fp64 add)
+__global__ void mtx_run_sum_kernel(const unsigned long long *__restrict__ key, const double *__restrict__ val,
+                                   const int *__restrict__ start, long long nRuns, long long n,
+                                   unsigned long long *__restrict__ okey, double *__restrict__ oval)
+{
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nRuns) return;
+    const long long b = start[h], e = h + 1 < nRuns ? start[h + 1] : n;
+    double acc = val[b];
+    for (long long j = b + 1; j < e; j++) acc = __dadd_rn(acc, val[j]);
+    okey[h] = key[b];
+    oval[h] = acc;
 }
 
 struct Parsed {
@@ -133,13 +155,22 @@ extern "C" int b200spmv_load_mtx(const char *path, int mode, b200spmv_coo *out, 
             B2_CUDA(cub::DeviceRadixSort::SortPairs(t.p, tmp, k0.p, k1.p, v0.p, v1.p, (int)n, 0, 64, s));
             B2_CUDA(cudaStreamSynchronize(s));
         }
-        if (mode == B200SPMV_MTX_BANNER) {              // duplicate coordinates are summed (in file order)
-            B2_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp, k1.p, k0.p, v1.p, v0.p, nout.p, cub::Sum(), (int)n, s));
+        if (mode == B200SPMV_MTX_BANNER) {              // duplicate coordinates are summed, strictly in file order
+            DevBuf<char> head;
+            DevBuf<int> start;
+            B2_TRY(head.alloc((size_t)n));
+            B2_TRY(start.alloc((size_t)n));
+            mtx_head_kernel<<<ceil_div(n, 256), 256, 0, s>>>(k1.p, n, head.p);
+            B2_KERNEL_CHECK();
+            thrust::counting_iterator<int> iota(0);
+            B2_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp, iota, head.p, start.p, nout.p, (int)n, s));
             DevBuf<char> t;
             B2_TRY(t.alloc(tmp));
-            B2_CUDA(cub::DeviceReduce::ReduceByKey(t.p, tmp, k1.p, k0.p, v1.p, v0.p, nout.p, cub::Sum(), (int)n, s));
+            B2_CUDA(cub::DeviceSelect::Flagged(t.p, tmp, iota, head.p, start.p, nout.p, (int)n, s));
             B2_CUDA(cudaMemcpyAsync(&nnz, nout.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
             B2_CUDA(cudaStreamSynchronize(s));
+            mtx_run_sum_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(k1.p, v1.p, start.p, nnz, n, k0.p, v0.p);
+            B2_KERNEL_CHECK();
             keys = k0.p;
             vals = v0.p;
         }

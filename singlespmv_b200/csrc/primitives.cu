@@ -1,4 +1,5 @@
 // primitives.cu -- error state and the device passes every conversion is composed of.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -103,6 +104,63 @@ template <typename T> static int exclusive_scan_t(const T *in_d, T *out_d, int n
 }
 int exclusive_scan_i32(const int *in_d, int *out_d, int n, cudaStream_t s) { return exclusive_scan_t(in_d, out_d, n, s); }
 int exclusive_scan_i64(const long long *in_d, long long *out_d, int n, cudaStream_t s) { return exclusive_scan_t(in_d, out_d, n, s); }
+
+// 64-bit sum of an int32 array (sizes that may pass 2^31); synchronises the stream
+__global__ void sum_i64_kernel(const int *__restrict__ in, int n, unsigned long long *out)
+{
+    long long v = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v += in[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
+}
+int sum_i32_as_i64(const int *in_d, int n, long long *out_h, cudaStream_t s)
+{
+    DevBuf<unsigned long long> acc;
+    B2_TRY(acc.alloc(1));
+    B2_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(unsigned long long), s));
+    if (n > 0) {
+        sum_i64_kernel<<<std::min(ceil_div(n, 256), 148 * 8), 256, 0, s>>>(in_d, n, acc.p);
+        B2_KERNEL_CHECK();
+    }
+    B2_CUDA(cudaMemcpyAsync(out_h, acc.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return B200SPMV_OK;
+}
+
+__global__ void minmax_kernel(const int *__restrict__ in, long long b, long long e, int *out)
+{
+    int mn = 0x7fffffff, mx = -0x7fffffff - 1;
+    for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
+        const int v = in[i];
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], mn);
+        atomicMax(&out[1], mx);
+    }
+}
+int minmax_i32(const int *in_d, long long b, long long e, int *mn_h, int *mx_h)
+{
+    DevBuf<int> o;
+    B2_TRY(o.alloc(2));
+    int init[2] = {0x7fffffff, -0x7fffffff - 1};
+    B2_CUDA(cudaMemcpy(o.p, init, sizeof init, cudaMemcpyHostToDevice));
+    if (e > b) {
+        minmax_kernel<<<(int)std::min<long long>((e - b + 255) / 256, 148 * 8), 256>>>(in_d, b, e, o.p);
+        B2_KERNEL_CHECK();
+    }
+    B2_CUDA(cudaMemcpy(init, o.p, sizeof init, cudaMemcpyDeviceToHost));
+    *mn_h = init[0];
+    *mx_h = init[1];
+    return B200SPMV_OK;
+}
 
 // ---------------------------------------------------------------- input contract
 __global__ void validate_kernel(const int *__restrict__ row, const int *__restrict__ col, int nnz,

@@ -221,6 +221,40 @@ static int faithful_fold(const DevBuf<int> &segs, const std::vector<int> &counts
     return B200SPMV_OK;
 }
 
+// options.profile (faithful mode): the reference's PROF_BEGIN/PROF_END pairs around the Mul and the Sum phase
+// (src/util.h:59-65, opt_ss.cpp:225-304) become CUDA events; the multiply then synchronises and the last call's
+// phase times are readable as scalars MulTime_ns / SumTime_ns.
+struct PhaseTimer {
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    long long mul_ns = 0, sum_ns = 0;
+    bool on = false;
+    ~PhaseTimer() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    int mark(int i, cudaStream_t s)
+    {
+        if (!on) return B200SPMV_OK;
+        if (!e[i]) B2_CUDA(cudaEventCreate(&e[i]));
+        B2_CUDA(cudaEventRecord(e[i], s));
+        return B200SPMV_OK;
+    }
+    int finish()
+    {
+        if (!on) return B200SPMV_OK;
+        B2_CUDA(cudaEventSynchronize(e[2]));
+        float a = 0, b = 0;
+        B2_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+        B2_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+        mul_ns = (long long)(a * 1e6);
+        sum_ns = (long long)(b * 1e6);
+        return B200SPMV_OK;
+    }
+    bool scalar(const std::string &n, long long *out) const
+    {
+        if (n == "MulTime_ns") { *out = mul_ns; return true; }
+        if (n == "SumTime_ns") { *out = sum_ns; return true; }
+        return false;
+    }
+};
+
 // ================================================================= SS
 struct SsFormat : Format {
     int W, H = 0, nStep = 0, faithful, maxLen = 0;
@@ -229,9 +263,10 @@ struct SsFormat : Format {
     DevBuf<double> val2d, val_buf;
     std::vector<int> counts;
     TileStream ts;
+    PhaseTimer prof;
 
     int path_opt;
-    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful), path_opt(o.crs_path) {}
+    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful), path_opt(o.crs_path) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -241,8 +276,8 @@ struct SsFormat : Format {
         const long long slots = (long long)H * W;
         B2_TRY(row_ptr.alloc((size_t)nRow + 1));
         B2_TRY(row2d.alloc((size_t)slots));
-        B2_TRY(col2d.alloc((size_t)slots));
-        B2_TRY(val2d.alloc((size_t)slots));
+        B2_TRY(col2d.alloc((size_t)slots + SHORT_ROW_SLACK));       // slack: bulk copies of the short-row kernel end on 16 bytes
+        B2_TRY(val2d.alloc((size_t)slots + SHORT_ROW_SLACK));
         B2_TRY(seg_index.alloc((size_t)H));
         B2_TRY(build_row_ptr(A.row, nnz, nRow, row_ptr.p, s));
         if (slots) {
@@ -263,29 +298,43 @@ struct SsFormat : Format {
         if (!faithful) return multiply_rows(0, nRow, x, y, s);
         if (nRow == 0) return B200SPMV_OK;
         const long long slots = (long long)H * W;
+        B2_TRY(prof.mark(0, s));
         if (slots) {
             ss_mul_kernel<<<ceil_div(slots, 256), 256, 0, s>>>(col2d.p, val2d.p, x, slots, val_buf.p);
             B2_KERNEL_CHECK();
         }
+        B2_TRY(prof.mark(1, s));
         B2_TRY(faithful_fold(segs, counts, W, val_buf.p, s));
         ss_gather_kernel<<<ceil_div(nRow, 256), 256, 0, s>>>(row_ptr.p, val_buf.p, nRow, W, 0, y);
         B2_KERNEL_CHECK();
-        return B200SPMV_OK;
+        B2_TRY(prof.mark(2, s));
+        return prof.finish();
     }
 
     bool has_rows() const override { return !faithful; }
+    int prepare_rows(int rb, int re) override { return (faithful || short_rows) ? B200SPMV_OK : ts.prepare(rb, re); }
+    int col_extent(int rb, int re, int *cmin, int *cmax) override
+    {
+        if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        int pb = 0, pe = 0;
+        B2_CUDA(cudaMemcpy(&pb, row_ptr.p + rb, sizeof(int), cudaMemcpyDeviceToHost));
+        B2_CUDA(cudaMemcpy(&pe, row_ptr.p + re, sizeof(int), cudaMemcpyDeviceToHost));
+        if (pe <= pb) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
+        return minmax_i32(col2d.p, pb, pe, cmin, cmax);
+    }
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful) return Format::multiply_rows(rb, re, x, y, s);
         if (short_rows) {        // same fused product+sum, warp-per-32-rows stream (crs.cu)
             if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
-            return rowblock_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, s);
+            return short_row_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, s);
         }
         return ts.run_rows(x, y, false, rb, re, s);
     }
 
     bool scalar(const std::string &n, long long *out) override
     {
+        if (prof.scalar(n, out)) return true;
         if (n == "H") { *out = H; return true; }
         if (n == "nStep") { *out = nStep; return true; }
         if (n == "W") { *out = W; return true; }
@@ -307,8 +356,8 @@ struct SsFormat : Format {
     {
         if (n == "row_ptr") return export_device(row_ptr.p, row_ptr.bytes(), dst, cap);
         if (n == "row_idx") return export_device(row2d.p, row2d.bytes(), dst, cap);
-        if (n == "col_idx") return export_device(col2d.p, col2d.bytes(), dst, cap);
-        if (n == "val") return export_device(val2d.p, val2d.bytes(), dst, cap);
+        if (n == "col_idx") return export_device(col2d.p, sizeof(int) * (size_t)H * W, dst, cap);
+        if (n == "val") return export_device(val2d.p, sizeof(double) * (size_t)H * W, dst, cap);
         if (n == "segment_index") return export_device(seg_index.p, seg_index.bytes(), dst, cap);
         if (n == "sum_segs") return export_device(segs.p, segs.bytes(), dst, cap);
         if (n == "sum_segs_count") return export_host(counts.data(), counts.size() * sizeof(int), dst, cap);
@@ -368,8 +417,9 @@ struct CssFormat : Format {
     DevBuf<int> row_ptr, row2d, col2d, seg_index;      // row_ptr: [nBlock][nRow+1]
     DevBuf<double> val2d, val_buf;
     std::vector<std::unique_ptr<CssBlock>> blocks;
+    PhaseTimer prof;
 
-    explicit CssFormat(const b200spmv_options &o) : W(o.segment_width), nBlockWanted(o.n_block), faithful(o.ss_faithful) {}
+    explicit CssFormat(const b200spmv_options &o) : W(o.segment_width), nBlockWanted(o.n_block), faithful(o.ss_faithful) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -458,10 +508,12 @@ struct CssFormat : Format {
             return B200SPMV_OK;
         }
         const long long slots = (long long)totalH * W;
+        B2_TRY(prof.mark(0, s));
         if (slots) {
             ss_mul_kernel<<<ceil_div(slots, 256), 256, 0, s>>>(col2d.p, val2d.p, x, slots, val_buf.p);   // opt_css.cpp:226-240
             B2_KERNEL_CHECK();
         }
+        B2_TRY(prof.mark(1, s));
         B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
         for (int b = 0; b < nBlock; b++) {
             CssBlock &k = *blocks[(size_t)b];
@@ -470,10 +522,17 @@ struct CssFormat : Format {
                                                                 nRow, W, 1, y);                           // opt_css.cpp:298
             B2_KERNEL_CHECK();
         }
-        return B200SPMV_OK;
+        B2_TRY(prof.mark(2, s));
+        return prof.finish();
     }
 
     bool has_rows() const override { return !faithful; }
+    int prepare_rows(int rb, int re) override
+    {
+        if (faithful || (rb == 0 && re == nRow)) return B200SPMV_OK;
+        for (auto &k : blocks) B2_TRY(k->ts.prepare(rb, re));
+        return B200SPMV_OK;
+    }
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful) return Format::multiply_rows(rb, re, x, y, s);
@@ -502,6 +561,7 @@ struct CssFormat : Format {
 
     bool scalar(const std::string &n, long long *out) override
     {
+        if (prof.scalar(n, out)) return true;
         if (n == "B") { *out = B; return true; }
         if (n == "nBlock") { *out = nBlock; return true; }
         if (n == "totalH") { *out = totalH; return true; }

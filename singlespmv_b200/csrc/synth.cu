@@ -233,13 +233,16 @@ extern "C" int b200spmv_synth(int kind, long long p0, long long p1, unsigned lon
     B2_TRY(cnt.alloc((size_t)rows + 1));
     stencil_count_kernel<<<ceil_div((long long)rows + 1, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p);
     B2_KERNEL_CHECK();
-    // int32 offsets are enough unless the slice itself exceeds 2^31-1 entries: check with the closed form
+    // int32 offsets are enough unless the SLICE itself exceeds 2^31-1 entries (the global matrix may be larger: a
+    // row-partitioned run only ever generates one block per GPU).  rows x longest row bounds the slice; only when
+    // that bound overflows is the exact 64-bit sum of the slice's row lengths taken.
     {
-        const long long N = p0;
-        const long long total = kind == B200SPMV_SYNTH_LAP2D5 ? 5 * N * N - 4 * N
-                              : kind == B200SPMV_SYNTH_LAP3D7 ? 7 * N * N * N - 6 * N * N
-                                                              : (3 * N - 2) * (3 * N - 2) * (3 * N - 2);
-        if (total > 0x7fffffffLL) { set_error("synth: %lld entries exceed int32", total); return B200SPMV_ERR_INVALID; }
+        const long long perRow = kind == B200SPMV_SYNTH_LAP2D5 ? 5 : kind == B200SPMV_SYNTH_LAP3D7 ? 7 : 27;
+        if ((long long)rows * perRow > 0x7fffffffLL) {
+            long long total = 0;
+            B2_TRY(sum_i32_as_i64(cnt.p, rows, &total, s));
+            if (total > 0x7fffffffLL) { set_error("synth: the requested rows hold %lld entries, more than int32", total); return B200SPMV_ERR_INVALID; }
+        }
     }
     B2_TRY(exclusive_scan_i32(cnt.p, cnt.p, rows + 1, s));
     int nnz = 0;

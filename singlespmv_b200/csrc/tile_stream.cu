@@ -210,15 +210,36 @@ int TileStream::run_rows(const double *x, double *y, bool accumulate, int rb, in
     const auto key = std::make_pair(rb, re);
     auto it = range_cache.find(key);
     if (it == range_cache.end()) {
-        // tiles that hold any entry (or the shared position of empty rows) of rows [rb, re)
-        int pb = 0, pe = 0;
-        B2_CUDA(cudaMemcpy(&pb, row_ptr + rb, sizeof(int), cudaMemcpyDeviceToHost));
-        B2_CUDA(cudaMemcpy(&pe, row_ptr + re, sizeof(int), cudaMemcpyDeviceToHost));
-        const int lo = nTiles ? std::min(pb / tile, nTiles - 1) : 0;
-        const int hi = std::min(nTiles, pe / tile + 1);
-        it = range_cache.emplace(key, std::make_pair(lo, hi)).first;
+        // first use of this row range: two row pointers have to be read back.  b200spmv_prepare_rows() does this ahead
+        // of time; here it is refused during stream capture (a synchronous copy would invalidate the capture)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+            set_error("multiply_rows: row range [%d,%d) is used for the first time inside a stream capture; call "
+                      "b200spmv_prepare_rows() (or run one eager multiply_rows) first", rb, re);
+            return B200SPMV_ERR_STATE;
+        }
+        B2_TRY(prepare(rb, re));
+        it = range_cache.find(key);
     }
     return run(x, y, accumulate, rb, re, it->second.first, it->second.second, s);
+}
+
+// tiles that hold any entry (or the shared position of empty rows) of rows [rb, re); synchronous, cached
+int TileStream::prepare(int rb, int re)
+{
+    if (rb < 0 || re > nRow || rb > re) {
+        set_error("prepare_rows: bad row range [%d,%d) for %d rows", rb, re, nRow);
+        return B200SPMV_ERR_INVALID;
+    }
+    const auto key = std::make_pair(rb, re);
+    if (range_cache.count(key)) return B200SPMV_OK;
+    int pb = 0, pe = 0;
+    B2_CUDA(cudaMemcpy(&pb, row_ptr + rb, sizeof(int), cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemcpy(&pe, row_ptr + re, sizeof(int), cudaMemcpyDeviceToHost));
+    const int lo = nTiles ? std::min(pb / tile, nTiles - 1) : 0;
+    const int hi = std::min(nTiles, pe / tile + 1);
+    range_cache.emplace(key, std::make_pair(lo, hi));
+    return B200SPMV_OK;
 }
 
 int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo,

@@ -58,11 +58,16 @@ struct TileStream {
     }
     // rows [rb, re) only: looks up (and caches) the tiles that hold their entries
     int run_rows(const double *x, double *y, bool accumulate, int rb, int re, cudaStream_t s);
+    int prepare(int rb, int re);
     size_t meta_bytes() const { return tile_row.bytes(); }
     std::map<std::pair<int, int>, std::pair<int, int>> range_cache;
 };
 
-// short-row alternative to the tile-stream (crs.cu): warp-per-32-rows stream, no tiles, one launch
+// short-row alternatives to the tile-stream (crs.cu), one launch, every row bit-exact: the TMA-fed row-chunk stream
+// (default; idx and val need SHORT_ROW_SLACK entries of allocation slack) and the warp-per-32-rows row-block stream
+constexpr int SHORT_ROW_SLACK = 8;
+int short_row_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
+                   double *y, cudaStream_t s);
 int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
                   double *y, cudaStream_t s);
 bool rowblock_applies(int maxLen, long long nnz);

@@ -51,7 +51,8 @@ def plan_requests(halo_cols, bounds, rank, all_to_all_counts, all_to_all_lists):
 class Block:
     """One rank's share: local matrix (any format, default CRS), halo bookkeeping, device buffers."""
 
-    def __init__(self, kind, p0, p1, seed, bounds, rank, fmt="crs", stream=None):
+    def __init__(self, kind, p0, p1, seed, bounds, rank, fmt="crs", stream=None, crs_path=None):
+        import os
         import torch
         self.rank, self.bounds = rank, [int(b) for b in bounds]
         rb, re = self.bounds[rank], self.bounds[rank + 1]
@@ -65,10 +66,17 @@ class Block:
         check(lib.b200spmv_halo_info(self.halo, info))
         self.nLocal, self.nLeft, self.nRight, self.interiorBegin, self.interiorEnd = (int(v) for v in info[:5])
         self.nRows = re - rb
-        # the tile-stream kernel is the one whose CTAs (2048 entries, ~5 us) interleave well with the NCCL send/recv kernels
-        # inside the captured step: c5 at 8 GPUs, graph replay 0.419 ms with it, 0.538 ms with the row-block stream
-        self.A = SpMatOpt(fmt, crs_path=1 if fmt in ("crs", "ss") else 0).convert_device(coo, nRow=self.nRows, stream=stream)
+        # crs_path 0 = the library's own choice (short rows: the TMA-fed row-chunk stream, a persistent kernel with one
+        # CTA set per SM); 1 forces the tile-stream kernel, which round 1 used here because the row-block stream of that
+        # round interleaved badly with the NCCL kernels (profiles/r1_experiments.md).  B200SPMV_DIST_CRS_PATH overrides.
+        if crs_path is None:
+            crs_path = int(os.environ.get("B200SPMV_DIST_CRS_PATH", "0"))
+        self.A = SpMatOpt(fmt, crs_path=crs_path if fmt in ("crs", "ss") else 0).convert_device(coo, nRow=self.nRows, stream=stream)
         coo.free()
+        # row-range bookkeeping now, so that no multiply_rows ever synchronises (they are captured in a CUDA graph)
+        for rb_, re_ in ((self.interiorBegin, self.interiorEnd), (0, self.interiorBegin), (self.interiorEnd, self.nRows)):
+            if re_ > rb_:
+                self.A.prepare_rows(rb_, re_)
         n = lib.b200spmv_halo_cols(self.halo, None, 0)
         check(n)
         self.halo_cols = np.empty(n // 4, np.int32)
@@ -222,6 +230,73 @@ class DistSpmv:
         cur.wait_stream(self.comm)
         b.multiply_boundary(cptr)
 
+    # ---- host-semantics step: x_owned comes from a pinned host slice, y goes back to one, inside the step
+    def plan_host(self, max_chunks=8):
+        """Row chunks of the interior and the piece of x each needs (b200spmv_rows_col_extent): a banded block starts
+        multiplying while the rest of its x slice is still crossing PCIe, and y flows back chunk by chunk."""
+        import torch
+        b = self.block
+        ib, ie = b.interiorBegin, b.interiorEnd
+        n = max(1, min(max_chunks, (ie - ib) * 8 // (4 << 20)))
+        cuts = [ib + (((ie - ib) * c // n) & ~31) for c in range(n)] + [ie]
+        self.h_chunks = [(cuts[c], cuts[c + 1]) for c in range(n) if cuts[c + 1] > cuts[c]]
+        self.h_pieces = [((b.nLocal * k // n) & ~31) for k in range(n)] + [b.nLocal]
+        self.h_need = []
+        for rb, re in self.h_chunks:
+            lo, hi = b.A.col_extent(rb, re)
+            own = hi - b.nLeft                                   # local numbering: [left halo | owned | right halo]
+            k = 0
+            while k + 1 < n and self.h_pieces[k + 1] <= own:
+                k += 1
+            self.h_need.append(k if hi >= lo else -1)
+        self.h_in, self.h_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.h_ev_in = [torch.cuda.Event() for _ in range(n)]
+        self.h_ev_out = [torch.cuda.Event() for _ in range(len(self.h_chunks) + 1)]
+
+    def step_host(self, x_pin, y_pin):
+        """One multiply with host vectors: H2D of the owned x slice (pieces), exchange + multiply, D2H of the owned
+        y slice (chunks) -- all three overlapped; returns without synchronising (streams h_out / current hold the tail)."""
+        import torch
+        import torch.distributed as dist
+        b = self.block
+        cur = torch.cuda.current_stream()
+        cptr = C.c_void_p(cur.cuda_stream)
+        self.h_in.wait_stream(cur)                               # the previous step's readers of x_ext
+        cur.wait_stream(self.h_out)                              # the previous step's D2H of y
+        n = len(self.h_ev_in)
+        with torch.cuda.stream(self.h_in):
+            for k in range(n):
+                p0, p1 = self.h_pieces[k], self.h_pieces[k + 1]
+                if p1 > p0:
+                    b.x_owned[p0:p1].copy_(x_pin[p0:p1], non_blocking=True)
+                self.h_ev_in[k].record(self.h_in)
+        self.comm.wait_stream(cur)
+        self.comm.wait_event(self.h_ev_in[-1])                   # the send lists touch both ends of the slice
+        with torch.cuda.stream(self.comm):
+            b.pack(C.c_void_p(self.comm.cuda_stream))
+            ops = [dist.P2POp(dist.irecv, v, p) for p, v in b.recv_views.items()]
+            ops += [dist.P2POp(dist.isend, v, p) for p, v in b.send_views.items()]
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+        for i, (rb, re) in enumerate(self.h_chunks):
+            if self.h_need[i] >= 0:
+                cur.wait_event(self.h_ev_in[self.h_need[i]])
+            b.A.multiply_rows(rb, re, b.x_ext.data_ptr(), b.y.data_ptr(), cptr)
+            self.h_ev_out[i].record(cur)
+            self.h_out.wait_event(self.h_ev_out[i])
+            with torch.cuda.stream(self.h_out):
+                y_pin[rb:re].copy_(b.y[rb:re], non_blocking=True)
+        cur.wait_event(self.h_ev_in[-1])
+        cur.wait_stream(self.comm)
+        b.multiply_boundary(cptr)
+        self.h_ev_out[-1].record(cur)
+        self.h_out.wait_event(self.h_ev_out[-1])
+        with torch.cuda.stream(self.h_out):
+            if b.interiorBegin > 0:
+                y_pin[:b.interiorBegin].copy_(b.y[:b.interiorBegin], non_blocking=True)
+            if b.interiorEnd < b.nRows:
+                y_pin[b.interiorEnd:].copy_(b.y[b.interiorEnd:], non_blocking=True)
+
     def enable_graph(self, warmup=3):
         """Capture one step (both streams, the NCCL send/recv included) in a CUDA graph: one launch per step
         instead of ~8 kernel launches + a grouped NCCL call from Python.  Falls back to eager on any failure."""
@@ -267,7 +342,7 @@ def run_partitioned_bench(args, wl, wl_key):
     import time
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler, peaks
+    from bench import ClockSampler, CpuReferenceCrs, parity_of, peaks, sample_rows_for
 
     # NCCL prints its version banner on stdout; the contract is ONE JSON line there -> park fd 1 on stderr meanwhile
     sys.stdout.flush()
@@ -347,14 +422,33 @@ def run_partitioned_bench(args, wl, wl_key):
     eager_full_ms = timed(eng._step_eager)
     compute_only_ms = timed(compute_only)
 
-    # e2e: per step H2D of the owned x slice, exchange + multiply, D2H of the owned y slice
+    # sampled full-size parity: the first rows of the matrix (all inside rank 0's block) against the reference's CRS
+    parity = None
+    if rank == 0 and not getattr(args, "no_cpu", False):
+        import numpy as np
+        rows = min(sample_rows_for(wl), b.nRows)
+        c = DeviceCoo(wl["kind"], wl["p0"], wl["p1"], wl["seed"], 0, rows)
+        _, _, row, col, val = c.to_host()
+        c.free()
+        x_full, _ = reference_vectors(nRow, 0, 3)
+        ref = CpuReferenceCrs(rows, nRow, row, col, val, x_full)
+        ref.call()
+        mag = np.bincount(row, weights=np.abs(val * x_full[col]), minlength=rows)[:rows]
+        parity = dict(parity_of(b.y[:rows].cpu().numpy(), ref.y, mag),
+                      against="reference CRS (src/opt_crs.cpp:44-70) on the first rows of the same matrix (rank 0's block)")
+        del ref, row, col, val, x_full, mag
+    dist.barrier()
+
+    # e2e: per step H2D of the owned x slice, exchange + multiply, D2H of the owned y slice -- the three overlapped
+    # (x in pieces, y in chunks; DistSpmv.step_host)
+    eng.plan_host()
+
     def e2e_step():
-        b.x_owned.copy_(x_pin, non_blocking=True)
-        eng.step()
-        y_pin.copy_(b.y, non_blocking=True)
+        eng.step_host(x_pin, y_pin)
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
+    assert torch.equal(y_pin, b.y.cpu()), "host-semantics and device-resident results differ"
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -378,6 +472,8 @@ def run_partitioned_bench(args, wl, wl_key):
                 "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "nRow": nRow, "nCol": nRow, "nnz": nnz,
                            "parallelism": "row blocks by nnz balance x%d, x halo %d doubles/step over NCCL send/recv "
                                           "overlapped with interior rows" % (world, halo_total),
+                           "local_kernel": ("crs_tma_kernel (row-chunk stream)" if fmt == "crs" and b.A.scalar("short_row_path") else
+                                            "tile_stream_kernel" if fmt in ("crs", "ss", "css") else fmt),
                            "launch": "one CUDA graph per step (both streams + NCCL captured)" if graphed else "eager launches",
                            "eager_ms_per_step": eager_full_ms, "compute_only_ms_per_step": compute_only_ms,
                            "exposed_exchange_ms": max(0.0, eager_full_ms - compute_only_ms),
@@ -385,10 +481,12 @@ def run_partitioned_bench(args, wl, wl_key):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / (peak * world), "traffic": None,
                              "peak_source": peak_src + " x %d GPUs" % world, "alg_bytes_per_launch": alg_bytes,
-                             "kernel": "CRS multiply (crs_rowblock_kernel for short rows, else tile_stream_kernel): whole step incl. exposed halo exchange"},
+                             "kernel": "CRS multiply (crs_tma_kernel for short rows, else tile_stream_kernel): whole step incl. exposed halo exchange"},
                 "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
                         "h2d_bytes_per_step": 8 * nRow, "d2h_bytes_per_step": 8 * nRow},
                 "gpu_launches": int(launches.item()) * args.steps, "clocks": clocks}
+        if parity is not None:
+            line["parity"] = parity
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

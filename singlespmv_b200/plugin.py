@@ -149,6 +149,17 @@ class SpMatOpt:
     def multiply_rows(self, row_begin, row_end, x_ptr, y_ptr, stream=None):
         check(lib.b200spmv_multiply_rows(self.h, row_begin, row_end, C.c_void_p(x_ptr), C.c_void_p(y_ptr), stream))
 
+    def prepare_rows(self, row_begin, row_end):
+        """Host bookkeeping of a row range ahead of time, so that multiply_rows on it never synchronises
+        (needed before capturing it in a CUDA graph)."""
+        check(lib.b200spmv_prepare_rows(self.h, row_begin, row_end))
+
+    def col_extent(self, row_begin, row_end):
+        """(smallest, largest) column referenced by rows [row_begin, row_end); largest < smallest = empty rows."""
+        lo, hi = C.c_int(), C.c_int()
+        check(lib.b200spmv_rows_col_extent(self.h, row_begin, row_end, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def multiply_host(self, x, y):
         check(lib.b200spmv_multiply_host(self.h, _ptr(x), _ptr(y)))
 
@@ -184,6 +195,18 @@ def SpMV(A_opt, x_opt, y):
         raise B200SpmvError(-1, "SpMV: vector sizes %d/%d do not match the %dx%d matrix"
                             % (x_opt.size, y.size, A_opt.nRow, A_opt.nCol))
     A_opt.multiply_host(x_opt.val, y.val)
+
+
+def host_register(a):
+    """Page-lock a numpy array in place (what plugin/opt_b200.cpp does with the driver's x and y).  Returns False
+    when the driver refuses; the caller must keep `a` alive until host_unregister(a)."""
+    if a.nbytes == 0:
+        return False
+    return lib.b200spmv_host_register(_ptr(a), a.nbytes) == 0
+
+
+def host_unregister(a):
+    lib.b200spmv_host_unregister(_ptr(a))
 
 
 def reference_vectors(nCol, nRow, seed=3):

@@ -20,6 +20,10 @@
 #include "opt_b200.h"
 #include "util.h"
 
+extern std::vector<int> g_step_count;                                 // filled by the SS plugin (src/opt_ss.cpp:143-147)
+extern std::vector<double> g_step_time;
+extern std::vector<double> g_profile;
+
 #define DRV_CUDA(e) do { cudaError_t e_ = (e); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #e, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 static bool parse_synth (const std::string &arg, SpMat &A) {
@@ -73,6 +77,7 @@ int main (int argc, char **argv) {
 
 #ifndef B200_NO_VERIFY
     for (int i = 0; i < 2; i++) {                                         // src/main.cpp:40-56
+        g_profile = std::vector<double>(10);
         SpMV(A_opt, x_opt, y);
         B200FetchResult(A_opt, y);
         std::cerr << "Verifying " << i << " ... ";
@@ -90,6 +95,7 @@ int main (int argc, char **argv) {
     int loop = 1;
     std::cerr << "Calculating SpMV ... ";
     {
+        g_profile = std::vector<double>(10);
         const double t0 = GetTimeBySec();                                 // src/main.cpp:58-71
         do {
             for (int i = 0; i < loop; i++) SpMV(A_opt, x_opt, y);
@@ -98,12 +104,14 @@ int main (int argc, char **argv) {
         } while (GetTimeBySec() - t0 < minSeconds);
     }
     double minElapsedTime = 0;
+    std::vector<double> g_best_profile;
     {
         cudaEvent_t e0, e1;
         DRV_CUDA(cudaEventCreate(&e0));
         DRV_CUDA(cudaEventCreate(&e1));
         // src/main.cpp:79-102
         for (int t = 0; t < nTry; t++) {
+            g_profile = std::vector<double>(10);
             double elapsed;
 #ifdef B200_DEVICE_RESIDENT
             DRV_CUDA(cudaEventRecord(e0, (cudaStream_t)A_opt.stream));
@@ -119,7 +127,10 @@ int main (int argc, char **argv) {
             elapsed += GetTimeBySec();
             elapsed /= loop;
 #endif
-            if (t == 0 || elapsed < minElapsedTime) minElapsedTime = elapsed;
+            if (t == 0 || elapsed < minElapsedTime) {
+                minElapsedTime = elapsed;
+                g_best_profile = g_profile;
+            }
         }
     }
     std::cerr << "done." << std::endl;
@@ -134,8 +145,19 @@ int main (int argc, char **argv) {
     printf("%25s\t%s\n", "Architecture", "GPU");
     printf("%25s\t%s\n", "MatrixFormat", B200FormatName());
     printf("%25s\t%s\n", "Device", prop.name);
+    if (!strcmp(B200FormatName(), "SS")) {                                // src/main.cpp:155-162
+        printf("%25s\t%d\n", "nStep", int(g_step_count.size()));
+        for (size_t i = 0; i < g_step_count.size(); i++) printf("%22s-%02d\t%d\n", "StepCount", int(i), g_step_count[i]);
+    }
 #if defined(SEGMENT_WIDTH)
     printf("%25s\t%d\n", "SEGMENT_WIDTH(byte)", int(SEGMENT_WIDTH * sizeof(double)));
+#endif
+#if defined(PROFILING) && defined(B200_SS_FAITHFUL)
+    if (g_best_profile.size() >= 2 && g_best_profile[0] > 0 && g_best_profile[1] > 0) {   // src/main.cpp:171-174,184-187
+        const bool css = !strcmp(B200FormatName(), "CSS");
+        printf("%25s\t%lf\n", css ? "MulPerf(GFLOPS)" : "MulPerf", 2.0 * nNnz / (g_best_profile[0] / loop) / 1e9);
+        printf("%25s\t%lf\n", css ? "SumPerf(GFLOPS)" : "SumPerf", 2.0 * nNnz / (g_best_profile[1] / loop) / 1e9);
+    }
 #endif
 #if defined(N_BLOCK)
     printf("%25s\t%d\n", "N_BLOCK", N_BLOCK);
@@ -146,6 +168,7 @@ int main (int argc, char **argv) {
     printf("%25s\t%d\n", "nRow", nRow);
     printf("%25s\t%d\n", "nCol", nCol);
     printf("%25s\t%d\n", "nNnz", nNnz);
+    printf("%25s\t%d\n", "nThread", 1);                                   // host threads driving the device (src/main.cpp:200-206)
     printf("%25s\t%d\n", "nGPU", 1);
     printf("%25s\t%lf\n", "KernelTime(us)", minElapsedTime * 1e6);
     printf("%25s\t%lld\n", "AlgBytes", algBytes);

@@ -5,7 +5,14 @@
 #include "opt_b200.h"
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cuda_runtime_api.h>
+
+// report globals the SS / CSS plugins fill for the driver (defined in the host project's util.cpp:16-18,
+// read at src/main.cpp:157-174 and :83-98)
+extern std::vector<int> g_step_count;
+extern std::vector<double> g_step_time;
+extern std::vector<double> g_profile;
 
 #ifndef B200_FORMAT
 #define B200_FORMAT CRS
@@ -52,8 +59,27 @@ void OptimizeProblem (const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_o
 #ifdef B200_VALUE_F32
     opt.value_f32 = 1;              // CRS only: fp32 storage of the matrix values, fp64 arithmetic
 #endif
+#ifdef B200_SS_FAITHFUL
+    opt.ss_faithful = 1;            // SS / CSS: the reference's three-phase Mul / fold / gather schedule
+#ifdef PROFILING
+    opt.profile = 1;                // per-phase times -> g_profile[0] (Mul), g_profile[1] (Sum), src/opt_ss.cpp:225-304
+#endif
+#endif
     b200_check(b200spmv_create(B200_FORMAT_ENUM, &opt, &A_opt.handle), "create");
     b200_check(b200spmv_convert_coo_host(A_opt.handle, A.nRow, A.nCol, A.nNnz, A.row_idx, A.col_idx, A.val), "convert");
+    if (B200_FORMAT_ENUM == B200SPMV_SS) {          // src/opt_ss.cpp:143-147: one count per fold step for the report
+        const long long bytes = b200spmv_get_array(A_opt.handle, "sum_segs_count", NULL, 0);
+        g_step_count.assign(bytes > 0 ? (size_t)bytes / sizeof(int) : 0, 0);
+        if (bytes > 0) b200spmv_get_array(A_opt.handle, "sum_segs_count", g_step_count.data(), bytes);
+        g_step_time.assign(g_step_count.size(), 0.0);
+    }
+#ifndef B200_DEVICE_RESIDENT
+    // the driver's vectors are pageable (_mm_malloc, src/util.cpp:92-102): page-lock x now and y on the first SpMV so
+    // that the copies inside every SpMV are asynchronous DMA that overlaps the multiply.  Never fatal.
+    if (!getenv("B200_NO_HOST_REGISTER") && x.size > 0 &&
+        b200spmv_host_register(x.val, sizeof(double) * (unsigned long long)x.size) != B200SPMV_OK)
+        fprintf(stderr, "b200spmv: x stays pageable (%s)\n", b200spmv_last_error());
+#endif
 #ifdef B200_DEVICE_RESIDENT
     b200_cuda(cudaMalloc((void **)&A_opt.x_dev, sizeof(double) * (A.nCol > 0 ? A.nCol : 1)), "cudaMalloc x");
     b200_cuda(cudaMalloc((void **)&A_opt.y_dev, sizeof(double) * (A.nRow > 0 ? A.nRow : 1)), "cudaMalloc y");
@@ -67,7 +93,22 @@ void SpMV (const SpMatOpt &A, const VecOpt &x, Vec &y) {
     (void)x; (void)y;
     b200_check(b200spmv_multiply(A.handle, A.x_dev, A.y_dev, A.stream), "multiply");
 #else
+    static const double *registered_y = NULL;
+    if (registered_y != y.val && y.size > 0 && !getenv("B200_NO_HOST_REGISTER")) {
+        if (b200spmv_host_register(y.val, sizeof(double) * (unsigned long long)y.size) != B200SPMV_OK)
+            fprintf(stderr, "b200spmv: y stays pageable (%s)\n", b200spmv_last_error());
+        registered_y = y.val;
+    }
     b200_check(b200spmv_multiply_host(A.handle, x.val, y.val), "multiply");
+#endif
+#if defined(PROFILING) && defined(B200_SS_FAITHFUL)
+    if (g_profile.size() >= 2) {                      // PROF_BEGIN / PROF_END accumulate seconds (src/util.h:59-65)
+        long long mul = 0, sum = 0;
+        b200spmv_get_scalar(A.handle, "MulTime_ns", &mul);
+        b200spmv_get_scalar(A.handle, "SumTime_ns", &sum);
+        g_profile[0] += mul * 1e-9;
+        g_profile[1] += sum * 1e-9;
+    }
 #endif
 }
 }

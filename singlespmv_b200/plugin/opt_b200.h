@@ -9,6 +9,8 @@
 //     [-DSEGMENT_WIDTH=W] [-DN_BLOCK=N]   (same macros as src/param.h:9-20, used by SS / CSS)
 //     [-DB200_SIGMA=s]                    (CSR5 sigma, 0 = auto)
 //     [-DB200_VALUE_F32]                  (CRS: matrix values stored as fp32, arithmetic in fp64)
+//     [-DB200_SS_FAITHFUL [-DPROFILING]]  (SS / CSS: the reference's three-phase schedule; with PROFILING the Mul and
+//                                          Sum phase times go to g_profile[0] / [1] like src/opt_ss.cpp:225-304)
 //     [-DB200_DEVICE_RESIDENT]            (x stays in HBM, y is copied back only by B200FetchResult();
 //                                          default = host semantics like src/opt_cusparse.cpp:72-82)
 //

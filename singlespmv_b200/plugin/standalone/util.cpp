@@ -2,6 +2,13 @@
 // src/util.cpp (loader: first line not starting with '%' is "M N L", then exactly L "row col val"
 // triples, 1-based, sorted by (row, col), duplicates kept, banner/symmetry ignored).
 #include "util.h"
+#include <vector>
+
+// report globals written by the SS / CSS plugins (src/util.cpp:16-18)
+std::vector<int> g_step_count;
+std::vector<double> g_step_time;
+std::vector<double> g_profile;
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

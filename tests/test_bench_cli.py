@@ -23,7 +23,7 @@ def test_reference_arm_line():
     assert d["steps"] == 3 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0
-    assert d["config"]["workload"].startswith("c2:")
+    assert d["config"]["workload"].startswith("c5:") and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "rows" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
