@@ -582,6 +582,7 @@ def run_single(args, wl_key, only_format):
     # ---------------------------------------------------------------- every other config x named format
     if args.configs != "none" and not only_format:
         want = sorted(WORKLOADS) if args.configs == "all" else [c for c in args.configs.split(",") if c in WORKLOADS]
+        want = [c for c in want if c == wl_key] + [c for c in want if c != wl_key]     # the headline's matrix is loaded now
         steps2, warm2 = max(5, args.steps // 5), 3
         configs = {}
         for key in want:

@@ -74,12 +74,17 @@ typedef struct {
                             operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
     int value_f32;       /* CRS: 1 = store the matrix values as fp32 (rounded once at conversion); x, y and all
                             arithmetic stay fp64.  8 instead of 12 B/nnz; tolerance 1e-5 (BASELINE.json north star) */
-    int crs_path;        /* CRS / SS: 0 = choose from the longest row, 1 = always the tile-stream kernel,
-                            2 = row-block stream whenever it applies (longest row <= 16) */
+    int crs_path;        /* CRS / SS: 0 = choose from the longest row (<= 16: TMA-fed row-chunk stream, else tile-stream),
+                            1 = always the tile-stream kernel; when the short-row path applies: 2 = the warp-per-32-rows
+                            row-block stream of round 1, 3 = the TMA-fed row-chunk stream */
     int profile;         /* SS/CSS with ss_faithful: time the Mul and the Sum phase of every multiply with CUDA events
                             (the reference's -DPROFILING, src/util.h:59-65); the multiply then synchronises and the
                             scalars MulTime_ns / SumTime_ns hold the last call's phases */
-    int reserved[9];
+    int col_blocks;      /* ELL / JDS / SS: column-blocked compressed-slice device layout (csrc/cbs.cuh) for matrices whose
+                            gathers do not fit L2.  0 = decide from the matrix (x > 64 MB and rows spread over the column
+                            blocks), n > 0 = force n column blocks, -1 = never.  The reference arrays (exports) and y
+                            are the same either way: every row is still summed in ascending column order */
+    int reserved[8];
 } b200spmv_options;
 
 /* ---- library ---- */

@@ -263,9 +263,10 @@ bool rowchunk_preferred()
     return !(e && !strcmp(e, "rbs"));
 }
 int short_row_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
-                   double *y, cudaStream_t s)
+                   double *y, int kernel, cudaStream_t s)
 {
-    if (rowchunk_preferred() && maxLen <= 16) return rowchunk_spmv(ptr, idx, val, f32, maxLen, rb, re, x, y, s);
+    const bool tma = kernel == 3 || (kernel != 2 && rowchunk_preferred());
+    if (tma && maxLen <= 16) return rowchunk_spmv(ptr, idx, val, f32, maxLen, rb, re, x, y, s);
     return rowblock_spmv(ptr, idx, val, f32, maxLen, rb, re, x, y, s);
 }
 
@@ -312,7 +313,7 @@ struct CrsFormat : Format {
         if (!short_rows) return ts.run_rows(x, y, false, rb, re, s);
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
-        return short_row_spmv(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, maxLen, rb, re, x, y, s);
+        return short_row_spmv(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, maxLen, rb, re, x, y, path_opt, s);
     }
     bool has_rows() const override { return true; }
     int prepare_rows(int rb, int re) override { return short_rows ? B200SPMV_OK : ts.prepare(rb, re); }

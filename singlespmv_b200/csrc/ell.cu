@@ -3,6 +3,7 @@
 // slots :75-89).  Device layout = sliced ELL: slices of 32 rows (one warp), slice-local width
 // rounded to V slots, stored [slice][k/V][lane][V] so that a lane reads V column ids and V
 // values with 128-bit loads and a warp request is one contiguous 512 B / 1 KB run.
+#include "cbs.cuh"
 #include "common.cuh"
 
 namespace b2 {
@@ -138,6 +139,9 @@ struct EllFormat : Format {
     DevBuf<long long> slice_off;
     DevBuf<int> ecol;
     DevBuf<double> eval;
+    ColBlockSell cbs;                 // column-blocked compressed slices: the multiply layout when x does not fit L2
+    int cbs_want = 0;
+    explicit EllFormat(const b200spmv_options &o) : cbs_want(o.col_blocks) {}
 
     template <int VV> int convert_t(const CooView &A, const int *ptr, cudaStream_t s)
     {
@@ -176,16 +180,18 @@ struct EllFormat : Format {
         nSlices = ceil_div(nRow, 32);
         int st = V == 4 ? convert_t<4>(A, ptr.p, s) : convert_t<2>(A, ptr.p, s);
         B2_TRY(st);
+        B2_TRY(cbs.build(ptr.p, A.col, A.val, nRow, nCol, nnz, cbs_want, s));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
-    bool has_rows() const override { return true; }
+    bool has_rows() const override { return !cbs.active; }   // a row chunk would pay every column-block switch again
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
+        if (cbs.active) return Format::col_extent(rb, re, cmin, cmax);
         long long g[2] = {0, 0};                        // whole slices: padding columns (slot numbers) included
         B2_CUDA(cudaMemcpy(&g[0], slice_off.p + rb / 32, sizeof(long long), cudaMemcpyDeviceToHost));
         B2_CUDA(cudaMemcpy(&g[1], slice_off.p + ceil_div(re, 32), sizeof(long long), cudaMemcpyDeviceToHost));
@@ -197,6 +203,7 @@ struct EllFormat : Format {
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
+        if (cbs.active) return cbs.run(x, y, rb, re, s);
         const int sb = rb / 32, se = ceil_div(re, 32);
         const int blocks = ceil_div((long long)(se - sb) * 32, 256);
 #define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, rb, re, sb, se)
@@ -223,7 +230,8 @@ struct EllFormat : Format {
             *out = 12LL * slots + 8LL * (nSlices + 1) + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = 1; return true; }
+        if (n == "launches") { *out = cbs.active ? cbs.nBlock : 1; return true; }
+        if (n == "col_blocks") { *out = cbs.active ? cbs.nBlock : 0; return true; }
         return false;
     }
 
@@ -244,6 +252,6 @@ struct EllFormat : Format {
     }
 };
 
-Format *make_ell(const b200spmv_options &) { return new EllFormat(); }
+Format *make_ell(const b200spmv_options &o) { return new EllFormat(o); }
 
 }  // namespace b2

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cub/cub.cuh>
 
+#include "cbs.cuh"
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -264,9 +265,11 @@ struct SsFormat : Format {
     std::vector<int> counts;
     TileStream ts;
     PhaseTimer prof;
+    ColBlockSell cbs;                 // column-blocked compressed slices: the fused multiply's layout when x does not fit L2
+    int cbs_want;
 
     int path_opt;
-    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful), path_opt(o.crs_path) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
+    explicit SsFormat(const b200spmv_options &o) : W(o.segment_width), faithful(o.ss_faithful), cbs_want(o.col_blocks), path_opt(o.crs_path) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -288,6 +291,7 @@ struct SsFormat : Format {
         B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, s));
         B2_TRY(max_row_length(row_ptr.p, nRow, &maxLen, s));
         short_rows = path_opt != 1 && rowblock_applies(maxLen, nnz);
+        if (!faithful) B2_TRY(cbs.build(row_ptr.p, A.col, A.val, nRow, nCol, nnz, cbs_want, s));
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
@@ -311,8 +315,8 @@ struct SsFormat : Format {
         return prof.finish();
     }
 
-    bool has_rows() const override { return !faithful; }
-    int prepare_rows(int rb, int re) override { return (faithful || short_rows) ? B200SPMV_OK : ts.prepare(rb, re); }
+    bool has_rows() const override { return !faithful && !cbs.active; }
+    int prepare_rows(int rb, int re) override { return (faithful || short_rows || cbs.active) ? B200SPMV_OK : ts.prepare(rb, re); }
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
@@ -325,9 +329,10 @@ struct SsFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful) return Format::multiply_rows(rb, re, x, y, s);
+        if (cbs.active) return cbs.run(x, y, rb, re, s);
         if (short_rows) {        // same fused product+sum, warp-per-32-rows stream (crs.cu)
             if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
-            return short_row_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, s);
+            return short_row_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, path_opt, s);
         }
         return ts.run_rows(x, y, false, rb, re, s);
     }
@@ -335,6 +340,7 @@ struct SsFormat : Format {
     bool scalar(const std::string &n, long long *out) override
     {
         if (prof.scalar(n, out)) return true;
+        if (n == "col_blocks") { *out = cbs.active ? cbs.nBlock : 0; return true; }
         if (n == "H") { *out = H; return true; }
         if (n == "nStep") { *out = nStep; return true; }
         if (n == "W") { *out = W; return true; }
@@ -343,7 +349,7 @@ struct SsFormat : Format {
             return true;
         }
         if (n == "launches") {
-            if (!faithful) { *out = short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
+            if (!faithful) { *out = cbs.active ? cbs.nBlock : short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
             int l = 2;
             for (int c : counts) l += c > 0;
             *out = l;

@@ -66,8 +66,9 @@ struct TileStream {
 // short-row alternatives to the tile-stream (crs.cu), one launch, every row bit-exact: the TMA-fed row-chunk stream
 // (default; idx and val need SHORT_ROW_SLACK entries of allocation slack) and the warp-per-32-rows row-block stream
 constexpr int SHORT_ROW_SLACK = 8;
+// kernel: 0 = default (row-chunk stream), 2 = row-block stream, 3 = row-chunk stream  (options.crs_path)
 int short_row_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
-                   double *y, cudaStream_t s);
+                   double *y, int kernel, cudaStream_t s);
 int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
                   double *y, cudaStream_t s);
 bool rowblock_applies(int maxLen, long long nnz);

@@ -698,3 +698,162 @@ def test_full_size_uniform_and_rmat(sp):
         for y in ys[1:]:
             assert torch.all((y - ys[0]).abs() <= 1e-12 * ys[0].abs() + 1e-300)
         d.free()
+
+
+# ------------------------------------------------------------------------------------------ round 2 additions
+def _short_row_matrix(rng, nRow, nCol, max_len):
+    """Rows of 0..max_len entries (many empty, many full), sorted, duplicate-free."""
+    rows, cols = [], []
+    for r in range(nRow):
+        k = rng.random()
+        n = 0 if k < 0.15 else max_len if k < 0.4 else int(rng.integers(1, max_len + 1))
+        c = np.sort(rng.choice(nCol, size=n, replace=False))
+        rows.append(np.full(n, r))
+        cols.append(c)
+    row = np.concatenate(rows).astype(np.int32)
+    col = np.concatenate(cols).astype(np.int32)
+    return row, col, rng.standard_normal(len(row))
+
+
+@pytest.mark.parametrize("max_len", [1, 5, 8, 9, 16])
+def test_crs_short_row_kernels_bit_exact(sp, oracle, max_len):
+    """The three CRS kernels that can take a short-row matrix -- tile-stream (crs_path=1), row-block stream (2), TMA-fed
+    row-chunk stream (3, the default) -- all sum every row in the reference's order: bit-identical y, also on row
+    ranges that start and end off the kernels' chunk / 16-byte boundaries, with empty rows and an empty tail."""
+    import torch
+    rng = np.random.default_rng(100 + max_len)
+    nRow, nCol = 5003, 4097
+    row, col, val = _short_row_matrix(rng, nRow, nCol, max_len)
+    keep = row < nRow - 37                                   # trailing empty rows
+    row, col, val = row[keep], col[keep], val[keep]
+    x = rng.random(nCol)
+    y_ref = oracle.crs_result(nRow, row, col, val, x)
+    xd = torch.from_numpy(x).cuda()
+    for path in (1, 2, 3, 0):
+        for fmt in ("crs", "ss"):
+            A_opt, y = run_host(sp, fmt, nRow, nCol, row, col, val, x, crs_path=path)
+            assert np.array_equal(y, y_ref), (fmt, path)
+            yd = torch.full((nRow,), float("nan"), dtype=torch.float64, device="cuda")
+            cuts = [0, 3, 517, 518, 1031, 4000, nRow - 1, nRow]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                A_opt.multiply_rows(a, b, xd.data_ptr(), yd.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(yd.cpu().numpy(), y_ref), (fmt, path, "ranges")
+    A32, y32 = run_host(sp, "crs", nRow, nCol, row, col, val, x, value_f32=1, crs_path=3)
+    _, y32_tile = run_host(sp, "crs", nRow, nCol, row, col, val, x, value_f32=1, crs_path=1)
+    assert np.array_equal(y32, y32_tile)
+
+
+def test_ell_dense_row_never_reads_past_x(sp):
+    """the slots that round a slice up to the vector width used to carry col = k >= nCol when a row was
+    (nearly) dense.  x lives in a buffer followed by NaNs: any gather past x[nCol-1] would poison y (0 * NaN)."""
+    import torch
+    for nRow, nCol in ((6, 5), (40, 7), (3, 1), (65, 33)):
+        rows, cols = [np.full(nCol, 1)], [np.arange(nCol)]                # one dense row
+        rows.append(np.array([0]))
+        cols.append(np.array([nCol - 1]))
+        order = np.lexsort((np.concatenate(cols), np.concatenate(rows)))
+        row = np.concatenate(rows)[order].astype(np.int32)
+        col = np.concatenate(cols)[order].astype(np.int32)
+        val = np.arange(1, len(row) + 1, dtype=np.float64)
+        A_opt = sp.SpMatOpt("ell").convert_host(sp.SpMat(nRow, nCol, row, col, val))
+        assert A_opt.scalar("K") == nCol
+        buf = torch.full((nCol + 64,), float("nan"), dtype=torch.float64, device="cuda")
+        buf[:nCol] = torch.arange(1, nCol + 1, dtype=torch.float64)
+        yd = torch.full((nRow,), float("nan"), dtype=torch.float64, device="cuda")
+        A_opt.multiply(buf.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        x = np.arange(1, nCol + 1, dtype=np.float64)
+        y_ref = np.zeros(nRow)
+        np.add.at(y_ref, row, val * x[col])
+        assert np.all(np.isfinite(y)) and np.allclose(y, y_ref, rtol=1e-14), (nRow, nCol, y)
+        lcol = A_opt.array("col_idx", np.int32).reshape(nRow, nCol)
+        assert np.array_equal(lcol[2], np.arange(nCol))                   # empty row: padding col = k (opt_ell.cpp:48)
+
+
+@pytest.mark.parametrize("fmt,opt", [("crs", {}), ("crs", {"crs_path": 1}), ("css", {"n_block": 3}), ("ell", {}), ("dia", {}),
+                                     ("ss", {})])
+def test_host_multiply_pipeline_pinned(sp, oracle, fmt, opt):
+    """Page-locked host vectors (b200spmv_host_register, what plugin/opt_b200.cpp does): x goes up in pieces, a row
+    chunk starts when the pieces up to its largest column have landed, y comes back chunk by chunk.  Same bits as the
+    device-resident multiply, also when x changes between calls."""
+    nr, nc, row, col, val = oracle.stencil("lap2d5", 1100)
+    x = oracle.reference_vectors(nc, nr)[0]
+    A_opt = sp.SpMatOpt(fmt, **opt).convert_host(sp.SpMat(nr, nc, row, col, val))
+    xs = x.copy()
+    y = np.full(nr, np.nan)
+    assert sp.host_register(xs) and sp.host_register(y)
+    try:
+        for x2 in (x, x[::-1].copy(), np.full(nc, 0.25), x * 3.0 + 1.0):
+            xs[:] = x2
+            y[:] = np.nan
+            A_opt.multiply_host(xs, y)
+            y_ref = oracle.crs_result(nr, row, col, val, x2)
+            if fmt == "css":
+                assert_y(y, y_ref, row, col, val, x2, nr)
+            else:
+                assert np.array_equal(y, y_ref)
+    finally:
+        sp.host_unregister(xs)
+        sp.host_unregister(y)
+    lo, hi = A_opt.col_extent(0, 32 * 1100)
+    if fmt != "css":
+        assert lo == 0 and 33 * 1100 - 1 <= hi <= 33 * 1100 + 31        # 5-point stencil: rows < 32 n reach column < 33 n
+    else:
+        assert (lo, hi) == (0, nc - 1)
+
+
+def test_col_extent_random(sp, oracle):
+    rng = np.random.default_rng(5)
+    nRow, nCol = 700, 900
+    row, col, val = skewed_matrix(rng, nRow, nCol, 9)
+    for fmt in ("crs", "ss", "ell", "dia"):
+        A_opt = sp.SpMatOpt(fmt).convert_host(sp.SpMat(nRow, nCol, row, col, val))
+        for a, b in ((0, nRow), (10, 11), (100, 400), (699, 700), (5, 5)):
+            sel = (row >= a) & (row < b)
+            lo, hi = A_opt.col_extent(a, b)
+            if sel.any():
+                assert lo <= col[sel].min() and hi >= col[sel].max(), (fmt, a, b)
+                if fmt in ("crs", "ss"):
+                    assert (lo, hi) == (col[sel].min(), col[sel].max())
+            elif fmt in ("crs", "ss"):
+                assert hi < lo
+
+
+def test_multiply_rows_in_cuda_graph_after_prepare(sp, oracle):
+    """Tile-stream row ranges read two row pointers back on first use; prepare_rows does that ahead of time so the
+    range can be captured, and an unprepared range inside a capture is refused instead of breaking the capture."""
+    import torch
+    nr, nc, row, col, val = oracle.stencil("box3d27", 14)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    A_opt = sp.SpMatOpt("crs").convert_host(sp.SpMat(nr, nc, row, col, val))
+    assert A_opt.scalar("short_row_path") == 0
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
+    cuts = [0, 700, 701, 2000, nr]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        A_opt.prepare_rows(a, b)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        s = torch.cuda.current_stream().cuda_stream
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            A_opt.multiply_rows(a, b, xd.data_ptr(), yd.data_ptr(), s)
+        with pytest.raises(sp.B200SpmvError) as e:
+            A_opt.multiply_rows(5, 9, xd.data_ptr(), yd.data_ptr(), s)
+        assert e.value.status == -4
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(yd.cpu().numpy(), y_ref)
+
+
+def test_ss_css_profile_phases(sp, oracle):
+    """options.profile with ss_faithful: the reference's PROF_BEGIN/END pairs (src/opt_ss.cpp:225-304) as CUDA events."""
+    nr, nc, row, col, val = oracle.stencil("lap2d5", 300)
+    x = oracle.reference_vectors(nc, nr)[0]
+    for fmt, opt in (("ss", {"segment_width": 4}), ("css", {"segment_width": 4, "n_block": 2})):
+        A_opt, y = run_host(sp, fmt, nr, nc, row, col, val, x, ss_faithful=1, profile=1, **opt)
+        assert A_opt.scalar("MulTime_ns") > 0 and A_opt.scalar("SumTime_ns") > 0
+        B_opt, y2 = run_host(sp, fmt, nr, nc, row, col, val, x, ss_faithful=1, **opt)
+        assert np.array_equal(y, y2) and B_opt.scalar("MulTime_ns") == 0

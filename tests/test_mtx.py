@@ -107,6 +107,29 @@ def test_load_mtx_sums_duplicates(tmp_path):
 
 
 @pytest.mark.gpu
+def test_load_mtx_duplicates_sum_in_file_order(tmp_path):
+    """duplicates are added left to right in file order (a non-associative fp64 sum), exactly like a host
+    loop over the file -- not in whatever order a library reduction picks."""
+    import singlespmv_b200 as sp
+    rng = np.random.default_rng(11)
+    ents = []
+    for k in range(4000):
+        r, c = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        ents.append((r, c, float(rng.standard_normal() * 10.0 ** int(rng.integers(-8, 8)))))
+    p = tmp_path / "dups.mtx"
+    write(p, "%%MatrixMarket matrix coordinate real general", 40, 40, ents)
+    _, _, row, col, val = sp.DeviceCoo.from_mtx(p).to_host()
+    text = {}
+    for ln in open(p).read().splitlines()[3:]:               # banner, comment, size line
+        r, c, v = ln.split()
+        k = (int(r) - 1, int(c) - 1)
+        text[k] = text[k] + float(v) if k in text else float(v)
+    assert len(row) == len(text)
+    for r, c, v in zip(row, col, val):
+        assert v == text[(int(r), int(c))], (r, c)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["fixture_10x10", "fixture_random", "fixture_5x5", "mini_rmat_s9"])
 def test_load_mtx_reference_semantics(tmp_path, name):
     """Same triples the reference's loader produced for its own fixtures (goldens), whatever the banner says."""
