@@ -51,7 +51,8 @@ typedef enum {
     B200SPMV_DIA  = 4,   /* src/opt_dia.cpp  */
     B200SPMV_SS   = 5,   /* src/opt_ss.cpp   */
     B200SPMV_CSS  = 6,   /* src/opt_css.cpp  */
-    B200SPMV_CSR5 = 7    /* opt/.../CSR5_cuda */
+    B200SPMV_CSR5 = 7,   /* opt/.../CSR5_cuda */
+    B200SPMV_HYB  = 8    /* ELL + COO tail: named, never implemented upstream (CSR5_cuda/detail/common.h:22) */
 } b200spmv_format;
 
 typedef enum {
@@ -80,11 +81,13 @@ typedef struct {
     int profile;         /* SS/CSS with ss_faithful: time the Mul and the Sum phase of every multiply with CUDA events
                             (the reference's -DPROFILING, src/util.h:59-65); the multiply then synchronises and the
                             scalars MulTime_ns / SumTime_ns hold the last call's phases */
-    int col_blocks;      /* ELL / JDS / SS: column-blocked compressed-slice device layout (csrc/cbs.cuh) for matrices whose
+    int col_blocks;      /* ELL / JDS / SS: column-blocked device layout (csrc/colblocks.cuh) for matrices whose
                             gathers do not fit L2.  0 = decide from the matrix (x > 64 MB and rows spread over the column
                             blocks), n > 0 = force n column blocks, -1 = never.  The reference arrays (exports) and y
-                            are the same either way: every row is still summed in ascending column order */
-    int reserved[8];
+                            are the same either way: every row is still summed in ascending column order (rows of more
+                            than 64 entries per block: within the 1e-12 tolerance) */
+    int hyb_k;           /* HYB: width of the ELL part; 0 = the largest width that max(4096, nRow/3) rows still fill */
+    int reserved[7];
 } b200spmv_options;
 
 /* ---- library ---- */

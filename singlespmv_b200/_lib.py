@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200spmv.so")
 
-FORMATS = {"crs": 0, "coo": 1, "ell": 2, "jds": 3, "dia": 4, "ss": 5, "css": 6, "csr5": 7}
+FORMATS = {"crs": 0, "coo": 1, "ell": 2, "jds": 3, "dia": 4, "ss": 5, "css": 6, "csr5": 7, "hyb": 8}
 SYNTH = {"lap2d5": 0, "lap3d7": 1, "box3d27": 2, "uniform": 3, "rmat": 4}
 
 class B200SpmvError(RuntimeError):
@@ -21,7 +21,7 @@ class B200SpmvError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("segment_width", C.c_int), ("n_block", C.c_int), ("csr5_sigma", C.c_int),
-                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("reserved", C.c_int * 8)]
+                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("hyb_k", C.c_int), ("reserved", C.c_int * 7)]
 
 
 class Stats(C.Structure):

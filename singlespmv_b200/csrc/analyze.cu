@@ -135,5 +135,7 @@ extern "C" int b200spmv_recommend_format(const b200spmv_stats *st, b200spmv_opti
     }
     // near-uniform rows: padded slices cost little and the kernel is a pure stream (c4: above the copy peak)
     if (ellFill >= 0.9 && st->rowMax <= st->nCol) return B200SPMV_ELL;
+    // mostly uniform rows with a few long ones (ELL alone would store 10-100 % padding): ELL part + COO tail
+    if (ellFill > 0.5 && cv <= 0.5) return B200SPMV_HYB;
     return B200SPMV_CRS;
 }

@@ -54,6 +54,7 @@ static Format *make_format(int format, const b200spmv_options &o)
     case B200SPMV_SS: return make_ss(o);
     case B200SPMV_CSS: return make_css(o);
     case B200SPMV_CSR5: return make_csr5(o);
+    case B200SPMV_HYB: return make_hyb(o);
     default: return nullptr;
     }
 }

@@ -77,6 +77,11 @@ struct CooView {
     const double *val;       // device
 };
 
+// how a multiply over a row range treats what y already holds (shared by the tile-stream and the row-chunk stream)
+enum { CS_OVERWRITE = 0,           // y[r] = sum
+       CS_CONTINUE = 1,            // acc = y[r]; acc += a_ij x_j ...; y[r] = acc   (next column block of the SAME running sum)
+       CS_ADD = 2 };               // y[r] = y[r] + sum                            (CSS: block sums added, src/opt_css.cpp:298)
+
 struct Format {
     int nRow = 0, nCol = 0, nnz = 0;
     virtual ~Format() {}
@@ -118,6 +123,7 @@ Format *make_dia(const b200spmv_options &);
 Format *make_ss(const b200spmv_options &);
 Format *make_css(const b200spmv_options &);
 Format *make_csr5(const b200spmv_options &);
+Format *make_hyb(const b200spmv_options &);
 
 // ---------------------------------------------------------------- shared device passes (primitives.cu)
 // ptr[r] = first index i with row[i] >= r, ptr[nRow] = nnz  (reference src/opt_crs.cpp:27-33)

@@ -20,6 +20,10 @@ constexpr int COO_TILE = COO_THREADS * COO_IPT;
 constexpr int COO_LONG = 64;
 constexpr int COO_MAXLONG = COO_TILE / COO_LONG + 2;
 
+// ACC (the COO tail of HYB, hyb.cu): y already holds the first part of every row's sum; the runs CONTINUE it
+// (acc = y[r]; acc += ...; y[r] = acc), nothing is zero-filled, and a short run that crosses into the next tile is left
+// entirely to the fix-up kernel (it restarts from the untouched y[r]).
+template <bool ACC>
 __global__ void __launch_bounds__(COO_THREADS)
 coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
                 const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
@@ -71,6 +75,7 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
     }
     const int prev_row = t0 > 0 ? row[t0 - 1] : -1;
     const bool last_tile = t0 + n == nnz;
+    const int next_row = (ACC && !last_tile) ? row[t0 + n] : -1;
     __syncthreads();
     if (!fast) {
         for (int i = tid; i < n; i += COO_THREADS)
@@ -94,19 +99,27 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
                 end = rest ? min(n, w * 32 + __ffs(rest) - 1) : n;
             }
             const int r = srow[i];
-            const int before = i ? srow[i - 1] : prev_row;
-            for (int e = before + 1; e < r; e++) y[e] = 0.0;    // empty rows in front of this run (beta = 0)
+            if (!ACC) {
+                const int before = i ? srow[i - 1] : prev_row;
+                for (int e = before + 1; e < r; e++) y[e] = 0.0;    // empty rows in front of this run (beta = 0)
+            }
             if (end - i > COO_LONG) {
                 long_start[atomicAdd(&n_long, 1)] = i;
                 continue;
             }
-            double acc = 0.0;
+            if (ACC && end == n && next_row == r) {
+                // the run goes on in the next tile.  At most COO_LONG entries in all: the fix-up recomputes it from the
+                // untouched y[r]; longer: this piece is added now and the fix-up adds the carries of the other tiles
+                const int probe = t0 + n + (COO_LONG - (n - i));
+                if (!(probe < nnz && row[probe] == r)) continue;
+            }
+            double acc = ACC ? y[r] : 0.0;
             for (int j = i; j < end; j++) acc = __dadd_rn(acc, prod[j]);
             y[r] = acc;       // complete unless the run continues in the next tile (then the fix-up finishes it)
         }
     }
     if (tid == 0 && n > 0 && srow[0] == prev_row) long_start[atomicAdd(&n_long, 1)] = -1;   // carried-in piece
-    if (last_tile && n > 0)
+    if (!ACC && last_tile && n > 0)
         for (int e = srow[n - 1] + 1 + tid; e < nRow; e += COO_THREADS) y[e] = 0.0;          // trailing empty rows
     __syncthreads();
 
@@ -121,12 +134,13 @@ coo_tile_kernel(const int *__restrict__ row, const int *__restrict__ col, const 
         acc = warp_sum(acc);
         if (lane == 0) {
             if (s < 0) carry[t] = acc;
-            else y[r] = acc;
+            else y[r] = ACC ? y[r] + acc : acc;
         }
     }
 }
 
 // one thread per tile: finishes the row whose entries continue from the previous tile (first carrying tile only)
+template <bool ACC>
 __global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
                                  const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ carry,
                                  int nnz, int nTiles)
@@ -143,7 +157,7 @@ __global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restr
     while (e < nnz && e - t0 <= COO_LONG && row[e] == rc) e++;
     const bool whole = (b == 0 || row[b - 1] != rc) && (e == nnz || row[e] != rc);
     if (whole && e - b <= COO_LONG) {
-        double acc = 0.0;
+        double acc = ACC ? y[rc] : 0.0;
         for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn(val[j], x[col[j]]));
         y[rc] = acc;
     } else {
@@ -181,10 +195,10 @@ struct CooFormat : Format {
             B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
             return B200SPMV_OK;
         }
-        coo_tile_kernel<<<nTiles, COO_THREADS, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, 1);
+        coo_tile_kernel<false><<<nTiles, COO_THREADS, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, 1);
         B2_KERNEL_CHECK();
         if (nTiles > 1) {
-            coo_fixup_kernel<<<ceil_div(nTiles, 256), 256, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nTiles);
+            coo_fixup_kernel<false><<<ceil_div(nTiles, 256), 256, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nTiles);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -211,5 +225,22 @@ struct CooFormat : Format {
 };
 
 Format *make_coo(const b200spmv_options &) { return new CooFormat(); }
+
+// y[r] continues with the sorted triplets' products, run by run (HYB's COO tail, hyb.cu); carry: ceil(nnz / COO_TILE) doubles
+int coo_accumulate(const int *row, const int *col, const double *val, int nnz, int nRow, const double *x, double *y,
+                   double *carry, cudaStream_t s)
+{
+    if (nnz == 0) return B200SPMV_OK;
+    const int nTiles = ceil_div(nnz, COO_TILE);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
+    coo_tile_kernel<true><<<nTiles, COO_THREADS, 0, s>>>(row, col, val, x, y, carry, nnz, nRow, vec_ok);
+    B2_KERNEL_CHECK();
+    if (nTiles > 1) {
+        coo_fixup_kernel<true><<<ceil_div(nTiles, 256), 256, 0, s>>>(row, col, val, x, y, carry, nnz, nTiles);
+        B2_KERNEL_CHECK();
+    }
+    return B200SPMV_OK;
+}
+int coo_tile_entries() { return COO_TILE; }
 
 }  // namespace b2

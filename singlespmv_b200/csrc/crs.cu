@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "chunk_stream.cuh"
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -108,176 +109,15 @@ bool rowblock_applies(int maxLen, long long nnz)
     return nnz > 0 && maxLen <= lim;
 }
 
-// ---- short-row path, TMA-fed ("row-chunk stream"): the same rows the row-block stream takes, but the matrix arrives
-// through the TMA unit instead of through the threads' load pipeline.  A persistent CTA walks chunks of CT_TH consecutive
-// rows; the idx/val run of a chunk is contiguous, so ONE elected thread brings it into shared memory with two 1-D bulk
-// copies (cp.async.bulk + mbarrier transaction count, SASS UBLKCP) while all threads are still busy with the previous
-// chunk: S stages, up to S-1 chunks (S-1 x ~40 KB per CTA) in flight with no thread waiting on them.  The threads
-// spend their own loads on what cannot be bulk-copied: the row pointers (prefetched one chunk ahead in registers)
-// and the x gathers.  One thread per row, ascending column order, unfused mul/add -> bit-identical to
-// opt_crs.cpp:61-67 for every row.  Chunk starts are rounded down to 16 bytes for the bulk copy; the arrays are
-// allocated with a few entries of slack so the rounded-up end stays inside them.
-constexpr int CT_MAXSTAGES = 4;
-constexpr int CT_SLACK = SHORT_ROW_SLACK;   // entries of allocation slack behind idx / val (bulk copies end on a 16-byte boundary)
-
-template <typename VT, int MAXL, int TH>
-__global__ void __launch_bounds__(TH)
-crs_tma_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, const VT *__restrict__ val,
-               const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int nChunks, int capI,
-               int capV, int S)
-{
-    extern __shared__ __align__(128) unsigned char ct_smem[];
-    __shared__ __align__(8) uint64_t bar[CT_MAXSTAGES];
-    __shared__ int sbase[CT_MAXSTAGES];
-    constexpr int VA = 16 / (int)sizeof(VT);                   // values per 16 bytes
-    int *sidx = reinterpret_cast<int *>(ct_smem);
-    VT *sval = reinterpret_cast<VT *>(ct_smem + (size_t)S * capI * sizeof(int));
-    const int tid = threadIdx.x;
-    const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
-
-    // thread 0 only: bulk copies of chunk c (entries [b, e)) into stage s
-    auto issue = [&](int s, int b, int e) {
-        sbase[s] = b;
-        const int bI = b & ~3, eI = (e + 3) & ~3, bV = b & ~(VA - 1), eV = (e + VA - 1) & ~(VA - 1);
-        const uint32_t bytesI = (uint32_t)(eI - bI) * 4u, bytesV = (uint32_t)(eV - bV) * (uint32_t)sizeof(VT);
-        mbar_expect_tx(&bar[s], bytesI + bytesV);              // release: sbase[s] is visible to whoever passes the wait
-        if (bytesI) {
-            tma_load_1d(sidx + (size_t)s * capI, idx + bI, bytesI, &bar[s], pol_stream);
-            tma_load_1d(sval + (size_t)s * capV, val + bV, bytesV, &bar[s], pol_stream);
-        }
-    };
-    auto chunk_first = [&](long long c) { return (int)min((long long)rowEnd, (long long)rowBegin + c * TH); };
-
-    if (tid == 0)
-        for (int s = 0; s < S; s++) mbar_init(&bar[s], 1);
-    __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < S; s++) {
-            const long long c = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (c < nChunks) issue(s, ptr[chunk_first(c)], ptr[chunk_first(c + 1)]);
-        }
-    }
-    int r = chunk_first(blockIdx.x) + tid;
-    int p = ptr[min(r, rowEnd)], q = ptr[min(r + 1, rowEnd)];
-    int k = 0;
-    for (long long c = blockIdx.x; c < nChunks; c += gridDim.x, k++) {
-        const int s = k % S;
-        // prefetches that land while this chunk is being reduced: the bounds of the chunk issued at the end of this
-        // iteration (thread 0) and this thread's row pointers in the CTA's next chunk
-        const long long cIssue = c + (long long)S * gridDim.x, cNext = c + gridDim.x;
-        int nb = 0, ne = 0, pn = 0, qn = 0;
-        if (tid == 0 && cIssue < nChunks) {
-            nb = ptr[chunk_first(cIssue)];
-            ne = ptr[chunk_first(cIssue + 1)];
-        }
-        const int rn = chunk_first(cNext) + tid;
-        if (cNext < nChunks) {
-            pn = ptr[min(rn, rowEnd)];
-            qn = ptr[min(rn + 1, rowEnd)];
-        }
-        mbar_wait(&bar[s], (uint32_t)(k / S) & 1u);
-        const int b = sbase[s];
-        const int io = s * capI - (b & ~3) + p, vo = s * capV - (b & ~(VA - 1)) + p;
-        const int len = r < rowEnd ? q - p : 0;
-        double xs[MAXL];
-#pragma unroll
-        for (int j = 0; j < MAXL; j++)
-            if (j < len) xs[j] = ld_x(x + sidx[io + j], pol_x);
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < MAXL; j++)
-            if (j < len) acc = __dadd_rn(acc, __dmul_rn((double)sval[vo + j], xs[j]));
-        if (r < rowEnd) y[r] = acc;
-        __syncthreads();                                       // every thread is done with stage s
-        if (tid == 0 && cIssue < nChunks) issue(s, nb, ne);
-        r = rn; p = pn; q = qn;
-    }
-}
-
-struct CtConfig { int th, stages, blocks; };
-static CtConfig ct_config(int maxLen)
-{
-    static const int env_th = getenv("B200SPMV_TMA_R") ? atoi(getenv("B200SPMV_TMA_R")) : 0;
-    static const int env_s = getenv("B200SPMV_TMA_S") ? atoi(getenv("B200SPMV_TMA_S")) : 0;
-    static const int env_b = getenv("B200SPMV_TMA_CTAS") ? atoi(getenv("B200SPMV_TMA_CTAS")) : 0;
-    CtConfig c;
-    c.th = (env_th == 256 || env_th == 512 || env_th == 128) ? env_th : (maxLen <= 8 ? 512 : 256);
-    c.stages = (env_s >= 2 && env_s <= CT_MAXSTAGES) ? env_s : 2;
-    c.blocks = env_b > 0 ? env_b : 0;                            // CTAs per SM; 0 = what the occupancy calculator says
-    return c;
-}
-
-template <typename VT, int MAXL, int TH>
-static int ct_launch(const int *ptr, const int *idx, const VT *val, int maxLen, int rb, int re, const double *x, double *y,
-                     const CtConfig &cfg, cudaStream_t s)
-{
-    constexpr int VA = 16 / (int)sizeof(VT);
-    const int capI = (TH * maxLen + 8 + 3) & ~3, capV = (TH * maxLen + 2 * VA + VA - 1) & ~(VA - 1);
-    const size_t smem = (size_t)cfg.stages * ((size_t)capI * 4 + (size_t)capV * sizeof(VT));
-    auto kern = crs_tma_kernel<VT, MAXL, TH>;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        B2_CUDA(cudaGetDevice(&dev));
-        B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int perSm = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, TH, smem));
-    if (perSm < 1) { set_error("crs row-chunk stream: %zu bytes of shared memory do not fit", smem); return B200SPMV_ERR_UNSUPPORTED; }
-    if (cfg.blocks > 0) perSm = std::min(perSm, cfg.blocks);
-    const int nChunks = ceil_div(re - rb, TH);
-    const int grid = std::min(nChunks, sms * perSm);
-    kern<<<grid, TH, smem, s>>>(ptr, idx, val, x, y, rb, re, nChunks, capI, capV, cfg.stages);
-    B2_KERNEL_CHECK();
-    return B200SPMV_OK;
-}
-
-// y[rb..re) = A x, TMA-fed; requires maxLen <= 16 and CT_SLACK entries of slack behind idx and val
-int rowchunk_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
-                  double *y, cudaStream_t s)
-{
-    if (rb >= re) return B200SPMV_OK;
-    const CtConfig cfg = ct_config(maxLen);
-#define CT_GO(VT, MAXL, TH) return ct_launch<VT, MAXL, TH>(ptr, idx, static_cast<const VT *>(val), maxLen, rb, re, x, y, cfg, s)
-#define CT_GO_TH(VT, MAXL)                         \
-    do {                                           \
-        if (cfg.th == 512) CT_GO(VT, MAXL, 512);   \
-        else if (cfg.th == 128) CT_GO(VT, MAXL, 128); \
-        else CT_GO(VT, MAXL, 256);                 \
-    } while (0)
-    if (f32) {
-        if (maxLen <= 8) CT_GO_TH(float, 8);
-        else CT_GO_TH(float, 16);
-    } else {
-        if (maxLen <= 8) CT_GO_TH(double, 8);
-        else CT_GO_TH(double, 16);
-    }
-#undef CT_GO_TH
-#undef CT_GO
-}
-// which short-row kernel: B200SPMV_SHORT=rbs keeps the row-block stream (A/B experiments), default the TMA-fed one
-bool rowchunk_preferred()
-{
-    static const char *e = getenv("B200SPMV_SHORT");
-    return !(e && !strcmp(e, "rbs"));
-}
-int short_row_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
-                   double *y, int kernel, cudaStream_t s)
-{
-    const bool tma = kernel == 3 || (kernel != 2 && rowchunk_preferred());
-    if (tma && maxLen <= 16) return rowchunk_spmv(ptr, idx, val, f32, maxLen, rb, re, x, y, s);
-    return rowblock_spmv(ptr, idx, val, f32, maxLen, rb, re, x, y, s);
-}
-
 struct CrsFormat : Format {
     int maxLen = 0;
-    bool short_rows = false;
+    bool short_rows = false, use_rbs = false;
     DevBuf<int> ptr, idx;
     DevBuf<double> val;
     DevBuf<float> val32;
     bool f32;
     TileStream ts;
+    ChunkStream cs;
     int path_opt;
     explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0), path_opt(o.crs_path) {}
 
@@ -286,22 +126,26 @@ struct CrsFormat : Format {
         nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
         B2_TRY(validate_sorted_coo(A, s));
         B2_TRY(ptr.alloc((size_t)nRow + 1));
-        B2_TRY(idx.alloc((size_t)nnz + CT_SLACK));
+        B2_TRY(idx.alloc((size_t)nnz + CS_SLACK));
         B2_TRY(build_row_ptr(A.row, nnz, nRow, ptr.p, s));                      // opt_crs.cpp:27-33
         B2_CUDA(cudaMemcpyAsync(idx.p, A.col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));   // :29
         if (f32) {
             val.release();
-            B2_TRY(val32.alloc((size_t)nnz + CT_SLACK));
+            B2_TRY(val32.alloc((size_t)nnz + CS_SLACK));
             if (nnz) crs_to_f32_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(A.val, nnz, val32.p);
             B2_KERNEL_CHECK();
             B2_TRY(ts.build(ptr.p, idx.p, val32.p, true, nRow, nnz, s));
         } else {
-            B2_TRY(val.alloc((size_t)nnz + CT_SLACK));
+            B2_TRY(val.alloc((size_t)nnz + CS_SLACK));
             B2_CUDA(cudaMemcpyAsync(val.p, A.val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));   // :30
             B2_TRY(ts.build(ptr.p, idx.p, val.p, false, nRow, nnz, s));
         }
         B2_TRY(max_row_length(ptr.p, nRow, &maxLen, s));
-        short_rows = path_opt != 1 && rowblock_applies(maxLen, nnz);
+        B2_TRY(cs.build(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, nRow, nnz, maxLen, s));
+        // path: 1 = tile-stream always; 2 = round 1's row-block stream where it applies (longest row <= 16);
+        // otherwise the TMA-fed row-chunk stream when the rows are short enough, else the tile-stream
+        use_rbs = path_opt == 2 && rowblock_applies(maxLen, nnz);
+        short_rows = path_opt != 1 && (use_rbs || cs.ok);
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
@@ -310,10 +154,11 @@ struct CrsFormat : Format {
 
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
-        if (!short_rows) return ts.run_rows(x, y, false, rb, re, s);
+        if (!short_rows) return ts.run_rows(x, y, CS_OVERWRITE, rb, re, s);
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
-        return short_row_spmv(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, maxLen, rb, re, x, y, path_opt, s);
+        if (use_rbs) return rowblock_spmv(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, maxLen, rb, re, x, y, s);
+        return cs.run(x, y, rb, re, CS_OVERWRITE, s);
     }
     bool has_rows() const override { return true; }
     int prepare_rows(int rb, int re) override { return short_rows ? B200SPMV_OK : ts.prepare(rb, re); }

@@ -3,7 +3,7 @@
 // slots :75-89).  Device layout = sliced ELL: slices of 32 rows (one warp), slice-local width
 // rounded to V slots, stored [slice][k/V][lane][V] so that a lane reads V column ids and V
 // values with 128-bit loads and a warp request is one contiguous 512 B / 1 KB run.
-#include "cbs.cuh"
+#include "colblocks.cuh"
 #include "common.cuh"
 
 namespace b2 {
@@ -139,7 +139,7 @@ struct EllFormat : Format {
     DevBuf<long long> slice_off;
     DevBuf<int> ecol;
     DevBuf<double> eval;
-    ColBlockSell cbs;                 // column-blocked compressed slices: the multiply layout when x does not fit L2
+    std::unique_ptr<ColBlockEngine> cb;   // column-blocked multiply layout when x does not fit L2 (colblocks.cuh)
     int cbs_want = 0;
     explicit EllFormat(const b200spmv_options &o) : cbs_want(o.col_blocks) {}
 
@@ -180,18 +180,18 @@ struct EllFormat : Format {
         nSlices = ceil_div(nRow, 32);
         int st = V == 4 ? convert_t<4>(A, ptr.p, s) : convert_t<2>(A, ptr.p, s);
         B2_TRY(st);
-        B2_TRY(cbs.build(ptr.p, A.col, A.val, nRow, nCol, nnz, cbs_want, s));
+        B2_TRY(make_col_block_engine(A, ptr.p, cbs_want, s, &cb));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
-    bool has_rows() const override { return !cbs.active; }   // a row chunk would pay every column-block switch again
+    bool has_rows() const override { return !(cb != nullptr); }   // a row chunk would pay every column-block switch again
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) { *cmin = 0; *cmax = -1; return B200SPMV_OK; }
-        if (cbs.active) return Format::col_extent(rb, re, cmin, cmax);
+        if ((cb != nullptr)) return Format::col_extent(rb, re, cmin, cmax);
         long long g[2] = {0, 0};                        // whole slices: padding columns (slot numbers) included
         B2_CUDA(cudaMemcpy(&g[0], slice_off.p + rb / 32, sizeof(long long), cudaMemcpyDeviceToHost));
         B2_CUDA(cudaMemcpy(&g[1], slice_off.p + ceil_div(re, 32), sizeof(long long), cudaMemcpyDeviceToHost));
@@ -203,7 +203,7 @@ struct EllFormat : Format {
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
-        if (cbs.active) return cbs.run(x, y, rb, re, s);
+        if ((cb != nullptr)) return cb->run(x, y, rb, re, s);
         const int sb = rb / 32, se = ceil_div(re, 32);
         const int blocks = ceil_div((long long)(se - sb) * 32, 256);
 #define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, rb, re, sb, se)
@@ -230,8 +230,8 @@ struct EllFormat : Format {
             *out = 12LL * slots + 8LL * (nSlices + 1) + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = cbs.active ? cbs.nBlock : 1; return true; }
-        if (n == "col_blocks") { *out = cbs.active ? cbs.nBlock : 0; return true; }
+        if (n == "launches") { *out = (cb != nullptr) ? cb->n_blocks() : 1; return true; }
+        if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
         return false;
     }
 

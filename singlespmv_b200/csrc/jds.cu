@@ -8,7 +8,7 @@
 // libstdc++ does -- b200spmv_jds_set_perm_host() imposes a given order for bit-exact array parity.
 #include <cub/cub.cuh>
 
-#include "cbs.cuh"
+#include "colblocks.cuh"
 #include "common.cuh"
 
 namespace b2 {
@@ -130,7 +130,7 @@ struct JdsFormat : Format {
     DevBuf<double> jval;
     std::vector<int> user_perm;
     bool have_user_perm = false;
-    ColBlockSell cbs;                 // column-blocked compressed slices: the multiply layout when x does not fit L2
+    std::unique_ptr<ColBlockEngine> cb;   // column-blocked multiply layout when x does not fit L2 (colblocks.cuh)
     int cbs_want = 0;
     explicit JdsFormat(const b200spmv_options &o) : cbs_want(o.col_blocks) {}
 
@@ -203,7 +203,7 @@ struct JdsFormat : Format {
             jds_fill_kernel<<<gb, 256, 0, s>>>(ptr.p, A.col, A.val, perm.p, jptr.p, nRow, jcol.p, jval.p);
             B2_KERNEL_CHECK();
         }
-        B2_TRY(cbs.build(ptr.p, A.col, A.val, nRow, nCol, nnz, cbs_want, s));
+        B2_TRY(make_col_block_engine(A, ptr.p, cbs_want, s, &cb));
         nLong = 0;
         if (maxLength > JDS_LONG)
             B2_CUDA(cudaMemcpy(&nLong, cnt.p + JDS_LONG, sizeof(int), cudaMemcpyDeviceToHost));
@@ -214,9 +214,9 @@ struct JdsFormat : Format {
     int multiply(const double *x, double *y, cudaStream_t s) override
     {
         if (nRow == 0) return B200SPMV_OK;
-        // gather-bound matrices: same rows, same ascending-column sums, column block by column block (cbs.cuh); the
+        // gather-bound matrices: same rows, same ascending-column sums, column block by column block (colblocks.cuh); the
         // permutation only orders the reference arrays, y[row] does not depend on it
-        if (cbs.active) return cbs.run(x, y, 0, nRow, s);
+        if ((cb != nullptr)) return cb->run(x, y, 0, nRow, s);
         if (nLong > 0) {
             jds_spmv_long_kernel<<<ceil_div((long long)nLong * 32, 256), 256, 0, s>>>(jptr.p, jcol.p, jval.p, perm.p, x, y, nLong, maxLength);
             B2_KERNEL_CHECK();
@@ -236,8 +236,8 @@ struct JdsFormat : Format {
             *out = 12LL * nnz + 4LL * (maxLength + 1) + 4LL * nRow + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = cbs.active ? cbs.nBlock : (nLong > 0) + (nRow > nLong); return true; }
-        if (n == "col_blocks") { *out = cbs.active ? cbs.nBlock : 0; return true; }
+        if (n == "launches") { *out = (cb != nullptr) ? cb->n_blocks() : (nLong > 0) + (nRow > nLong); return true; }
+        if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
         return false;
     }
 

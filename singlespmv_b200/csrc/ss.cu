@@ -20,9 +20,11 @@
 // (profiles/r1_experiments.md).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <cub/cub.cuh>
 
-#include "cbs.cuh"
+#include "chunk_stream.cuh"
+#include "colblocks.cuh"
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -264,8 +266,10 @@ struct SsFormat : Format {
     DevBuf<double> val2d, val_buf;
     std::vector<int> counts;
     TileStream ts;
+    ChunkStream cs;
+    bool use_rbs = false;
     PhaseTimer prof;
-    ColBlockSell cbs;                 // column-blocked compressed slices: the fused multiply's layout when x does not fit L2
+    std::unique_ptr<ColBlockEngine> cb;   // column-blocked multiply layout when x does not fit L2 (colblocks.cuh)
     int cbs_want;
 
     int path_opt;
@@ -279,8 +283,8 @@ struct SsFormat : Format {
         const long long slots = (long long)H * W;
         B2_TRY(row_ptr.alloc((size_t)nRow + 1));
         B2_TRY(row2d.alloc((size_t)slots));
-        B2_TRY(col2d.alloc((size_t)slots + SHORT_ROW_SLACK));       // slack: bulk copies of the short-row kernel end on 16 bytes
-        B2_TRY(val2d.alloc((size_t)slots + SHORT_ROW_SLACK));
+        B2_TRY(col2d.alloc((size_t)slots + CS_SLACK));       // slack: bulk copies of the row-chunk stream end on 16 bytes
+        B2_TRY(val2d.alloc((size_t)slots + CS_SLACK));
         B2_TRY(seg_index.alloc((size_t)H));
         B2_TRY(build_row_ptr(A.row, nnz, nRow, row_ptr.p, s));
         if (slots) {
@@ -290,8 +294,11 @@ struct SsFormat : Format {
         B2_TRY(build_chain(row2d.p, H, W, seg_index.p, &nStep, counts, segs, s));
         B2_TRY(ts.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, s));
         B2_TRY(max_row_length(row_ptr.p, nRow, &maxLen, s));
-        short_rows = path_opt != 1 && rowblock_applies(maxLen, nnz);
-        if (!faithful) B2_TRY(cbs.build(row_ptr.p, A.col, A.val, nRow, nCol, nnz, cbs_want, s));
+        B2_TRY(cs.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, maxLen, s));
+        use_rbs = path_opt == 2 && rowblock_applies(maxLen, nnz);
+        short_rows = path_opt != 1 && (use_rbs || cs.ok);
+        cb.reset();
+        if (!faithful) B2_TRY(make_col_block_engine(A, row_ptr.p, cbs_want, s, &cb));
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
@@ -315,8 +322,8 @@ struct SsFormat : Format {
         return prof.finish();
     }
 
-    bool has_rows() const override { return !faithful && !cbs.active; }
-    int prepare_rows(int rb, int re) override { return (faithful || short_rows || cbs.active) ? B200SPMV_OK : ts.prepare(rb, re); }
+    bool has_rows() const override { return !faithful && !(cb != nullptr); }
+    int prepare_rows(int rb, int re) override { return (faithful || short_rows || (cb != nullptr)) ? B200SPMV_OK : ts.prepare(rb, re); }
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
@@ -329,18 +336,19 @@ struct SsFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful) return Format::multiply_rows(rb, re, x, y, s);
-        if (cbs.active) return cbs.run(x, y, rb, re, s);
+        if ((cb != nullptr)) return cb->run(x, y, rb, re, s);
         if (short_rows) {        // same fused product+sum, warp-per-32-rows stream (crs.cu)
             if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
-            return short_row_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, path_opt, s);
+            if (use_rbs) return rowblock_spmv(row_ptr.p, col2d.p, val2d.p, false, maxLen, rb, re, x, y, s);
+            return cs.run(x, y, rb, re, CS_OVERWRITE, s);
         }
-        return ts.run_rows(x, y, false, rb, re, s);
+        return ts.run_rows(x, y, CS_OVERWRITE, rb, re, s);
     }
 
     bool scalar(const std::string &n, long long *out) override
     {
         if (prof.scalar(n, out)) return true;
-        if (n == "col_blocks") { *out = cbs.active ? cbs.nBlock : 0; return true; }
+        if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
         if (n == "H") { *out = H; return true; }
         if (n == "nStep") { *out = nStep; return true; }
         if (n == "W") { *out = W; return true; }
@@ -349,7 +357,7 @@ struct SsFormat : Format {
             return true;
         }
         if (n == "launches") {
-            if (!faithful) { *out = cbs.active ? cbs.nBlock : short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
+            if (!faithful) { *out = (cb != nullptr) ? cb->n_blocks() : short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
             int l = 2;
             for (int c : counts) l += c > 0;
             *out = l;
@@ -409,16 +417,52 @@ __global__ void css_scatter_kernel(const int *__restrict__ row, const int *__res
     val2d[p] = val[i];
 }
 
+__global__ void colblock_spread_kernel(const int *__restrict__ ptr, const int *__restrict__ col, int nRow, int B,
+                                       unsigned long long *__restrict__ stats)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int touched = 0, nonEmpty = 0;
+    if (r < nRow) {
+        int last = -1;
+        for (int j = ptr[r]; j < ptr[r + 1]; j++) {
+            const int b = col[j] / B;
+            touched += b != last;
+            last = b;
+        }
+        nonEmpty = touched > 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        touched += __shfl_xor_sync(0xffffffffu, touched, o);
+        nonEmpty += __shfl_xor_sync(0xffffffffu, nonEmpty, o);
+    }
+    if ((threadIdx.x & 31) == 0 && touched) {
+        atomicAdd(&stats[0], (unsigned long long)touched);
+        atomicAdd(&stats[1], (unsigned long long)nonEmpty);
+    }
+}
+
 struct CssBlock {
-    int H = 0, nStep = 0, cnt = 0;
+    int H = 0, nStep = 0, cnt = 0, maxLen = 0;
     long long base = 0;                  // first slab slot of the block
     std::vector<int> counts;
     DevBuf<int> segs;
     TileStream ts;
+    ChunkStream cs;                      // TMA-fed row-chunk stream when the block's rows are short enough
+    // acc: CS_OVERWRITE / CS_CONTINUE / CS_ADD.  gather_bound: the blocks exist because x does not fit L2 -- there the
+    // tile-stream kernel wins (2048 threads per SM keep more gathers in flight: c2, 2.92 ms against 4.43 ms for the
+    // row-chunk stream, profiles/r2_experiments.md); on short-row blocks of local matrices the row-chunk stream does
+    int run(const double *x, double *y, int rb, int re, bool gather_bound, int acc, cudaStream_t s)
+    {
+        if (cs.ok && !gather_bound) return cs.run(x, y, rb, re, acc, s);
+        return ts.run_rows(x, y, acc, rb, re, s);
+    }
 };
 
 struct CssFormat : Format {
     int W, nBlockWanted, faithful;
+    bool lean = false;                   // column-block engine of another format: W = 1, no chain metadata, no row slab
+    bool gather_bound = false;           // rows spread over the column blocks (decided at conversion): tile-stream per block
     int B = 0, nBlock = 0, totalH = 0;
     DevBuf<int> row_ptr, row2d, col2d, seg_index;      // row_ptr: [nBlock][nRow+1]
     DevBuf<double> val2d, val_buf;
@@ -426,11 +470,12 @@ struct CssFormat : Format {
     PhaseTimer prof;
 
     explicit CssFormat(const b200spmv_options &o) : W(o.segment_width), nBlockWanted(o.n_block), faithful(o.ss_faithful) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
+    bool input_checked = false;          // lean: the owning format validated the COO already
 
     int convert(const CooView &A, cudaStream_t s) override
     {
         nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
-        B2_TRY(validate_sorted_coo(A, s));
+        if (!input_checked) B2_TRY(validate_sorted_coo(A, s));
         blocks.clear();
         B = nCol > 0 ? (nCol + nBlockWanted - 1) / nBlockWanted : 1;       // ceil(nCol / N_BLOCK), opt_css.cpp:34
         if (B < 1) B = 1;
@@ -469,16 +514,17 @@ struct CssFormat : Format {
             blk->base = base[(size_t)b];
             start[(size_t)b + 1] = start[(size_t)b] + blk->cnt;
             base[(size_t)b + 1] = base[(size_t)b] + (long long)blk->H * W;
+            if (lean) base[(size_t)b + 1] = (base[(size_t)b + 1] + 3) & ~3LL;      // 16-byte aligned block starts (vector / bulk loads)
             totalH += blk->H;
             blocks.push_back(std::move(blk));
         }
-        const long long slots = (long long)totalH * W;
+        const long long slots = lean ? base[(size_t)nBlock] : (long long)totalH * W;
         B2_CUDA(cudaMemcpyAsync(blockStart.p, start.data(), sizeof(int) * ((size_t)nBlock + 1), cudaMemcpyHostToDevice, s));
         B2_CUDA(cudaMemcpyAsync(slabBase.p, base.data(), sizeof(long long) * ((size_t)nBlock + 1), cudaMemcpyHostToDevice, s));
         B2_TRY(row2d.alloc((size_t)slots));
-        B2_TRY(col2d.alloc((size_t)slots));
-        B2_TRY(val2d.alloc((size_t)slots));
-        B2_TRY(seg_index.alloc((size_t)totalH));
+        B2_TRY(col2d.alloc((size_t)slots + CS_SLACK));                      // slack: the row-chunk stream's copies end on 16 bytes
+        B2_TRY(val2d.alloc((size_t)slots + CS_SLACK));
+        B2_TRY(seg_index.alloc(lean ? 0 : (size_t)totalH));
         B2_TRY(row_ptr.alloc((size_t)nBlock * ((size_t)nRow + 1)));
         B2_CUDA(cudaMemsetAsync(row2d.p, 0, row2d.bytes(), s));             // padding: row = 0, col = 0, val = 0 (opt_css.cpp:103)
         B2_CUDA(cudaMemsetAsync(col2d.p, 0, col2d.bytes(), s));
@@ -493,9 +539,27 @@ struct CssFormat : Format {
             CssBlock &k = *blocks[(size_t)b];
             int *rp = row_ptr.p + (size_t)b * ((size_t)nRow + 1);
             B2_TRY(build_row_ptr(row2d.p + k.base, k.cnt, nRow, rp, s));
-            B2_TRY(build_chain(row2d.p + k.base, k.H, W, seg_index.p + seg0, &k.nStep, k.counts, k.segs, s));
+            if (!lean) B2_TRY(build_chain(row2d.p + k.base, k.H, W, seg_index.p + seg0, &k.nStep, k.counts, k.segs, s));
             B2_TRY(k.ts.build(rp, col2d.p + k.base, val2d.p + k.base, false, nRow, k.cnt, s));
+            B2_TRY(max_row_length(rp, nRow, &k.maxLen, s));
+            B2_TRY(k.cs.build(rp, col2d.p + k.base, val2d.p + k.base, false, nRow, k.cnt, k.maxLen, s));
             seg0 += k.H;
+        }
+        if (lean) { B2_CUDA(cudaStreamSynchronize(s)); row2d.release(); }
+        if (!lean && nBlock > 1 && nnz > 0) {
+            // several column blocks: do the rows really spread over them (x gathers from everywhere), or is the matrix local?
+            DevBuf<int> ptr;
+            DevBuf<unsigned long long> stats;
+            B2_TRY(ptr.alloc((size_t)nRow + 1));
+            B2_TRY(stats.alloc(2));
+            B2_TRY(build_row_ptr(A.row, nnz, nRow, ptr.p, s));
+            B2_CUDA(cudaMemsetAsync(stats.p, 0, stats.bytes(), s));
+            colblock_spread_kernel<<<ceil_div(nRow, 256), 256, 0, s>>>(ptr.p, A.col, nRow, B, stats.p);
+            B2_KERNEL_CHECK();
+            unsigned long long st[2] = {0, 0};
+            B2_CUDA(cudaMemcpyAsync(st, stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+            gather_bound = (double)st[0] >= 1.5 * (double)st[1];
         }
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
@@ -510,7 +574,7 @@ struct CssFormat : Format {
             return B200SPMV_OK;
         }
         if (!faithful) {
-            for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->ts.run_all(x, y, b > 0, s));
+            for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->run(x, y, 0, nRow, gather_bound, b > 0 ? CS_ADD : CS_OVERWRITE, s));
             return B200SPMV_OK;
         }
         const long long slots = (long long)totalH * W;
@@ -536,7 +600,7 @@ struct CssFormat : Format {
     int prepare_rows(int rb, int re) override
     {
         if (faithful || (rb == 0 && re == nRow)) return B200SPMV_OK;
-        for (auto &k : blocks) B2_TRY(k->ts.prepare(rb, re));
+        for (auto &k : blocks) if (!k->cs.ok) B2_TRY(k->ts.prepare(rb, re));
         return B200SPMV_OK;
     }
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
@@ -548,7 +612,20 @@ struct CssFormat : Format {
             B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
             return B200SPMV_OK;
         }
-        for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->ts.run_rows(x, y, b > 0, rb, re, s));
+        for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->run(x, y, rb, re, gather_bound, b > 0 ? CS_ADD : CS_OVERWRITE, s));
+        return B200SPMV_OK;
+    }
+    // the running-sum variant used by the column-block engine of ELL / JDS / SS: block b continues the sums block b-1
+    // left in y, so rows of up to TS_LONG entries per block are summed strictly in ascending column order
+    int multiply_continue(int rb, int re, const double *x, double *y, cudaStream_t s)
+    {
+        bool first = true;
+        for (auto &k : blocks) {
+            if (k->cnt == 0 && !first) continue;
+            if (k->cnt == 0) { B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s)); first = false; continue; }
+            B2_TRY(k->run(x, y, rb, re, gather_bound, first ? CS_OVERWRITE : CS_CONTINUE, s));
+            first = false;
+        }
         return B200SPMV_OK;
     }
 
@@ -562,7 +639,7 @@ struct CssFormat : Format {
     int multiply_rows_slice(int i, int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful || nBlock < 1) return multiply_rows(rb, re, x, y, s);
-        return blocks[(size_t)i]->ts.run_rows(x, y, i > 0, rb, re, s);
+        return blocks[(size_t)i]->run(x, y, rb, re, gather_bound, i > 0 ? CS_ADD : CS_OVERWRITE, s);
     }
 
     bool scalar(const std::string &n, long long *out) override
@@ -578,7 +655,7 @@ struct CssFormat : Format {
         }
         if (n == "launches") {
             long long l = 0;
-            if (!faithful) for (auto &k : blocks) l += k->ts.nTiles > 1 ? 2 : 1;
+            if (!faithful) for (auto &k : blocks) l += k->cs.ok ? 1 : (k->ts.nTiles > 1 ? 2 : 1);
             else { l = 2; for (auto &k : blocks) { l += 1; for (int c : k->counts) l += c > 0; } }
             *out = l;
             return true;
@@ -590,8 +667,8 @@ struct CssFormat : Format {
     {
         if (n == "row_ptr") return export_device(row_ptr.p, row_ptr.bytes(), dst, cap);
         if (n == "row_idx") return export_device(row2d.p, row2d.bytes(), dst, cap);
-        if (n == "col_idx") return export_device(col2d.p, col2d.bytes(), dst, cap);
-        if (n == "val") return export_device(val2d.p, val2d.bytes(), dst, cap);
+        if (n == "col_idx") return export_device(col2d.p, sizeof(int) * (size_t)totalH * W, dst, cap);
+        if (n == "val") return export_device(val2d.p, sizeof(double) * (size_t)totalH * W, dst, cap);
         if (n == "segment_index") return export_device(seg_index.p, seg_index.bytes(), dst, cap);
         std::vector<int> h;
         if (n == "H") { for (auto &k : blocks) h.push_back(k->H); return export_host(h.data(), h.size() * sizeof(int), dst, cap); }
@@ -620,5 +697,46 @@ struct CssFormat : Format {
 };
 
 Format *make_css(const b200spmv_options &o) { return new CssFormat(o); }
+
+// ================================================================= column-block engine for ELL / JDS / SS (colblocks.cuh)
+struct CrsColBlocks : ColBlockEngine {
+    CssFormat css;
+    explicit CrsColBlocks(const b200spmv_options &o) : css(o) { css.lean = true; css.input_checked = true; }
+    int run(const double *x, double *y, int rb, int re, cudaStream_t s) override { return css.multiply_continue(rb, re, x, y, s); }
+    int n_blocks() const override { return css.nBlock; }
+    const char *name() const override { return "crs"; }
+};
+int make_col_block_engine(const CooView &A, const int *row_ptr, int want, cudaStream_t s, std::unique_ptr<ColBlockEngine> *out)
+{
+    out->reset();
+    static const char *env_n = getenv("B200SPMV_COL_BLOCKS");           // experiments: 0 = never, n = n blocks
+    if (env_n) want = atoi(env_n) == 0 ? -1 : atoi(env_n);
+    if (want < 0 || A.nnz == 0 || A.nRow == 0 || A.nCol == 0) return B200SPMV_OK;
+    int nb = want;
+    if (want == 0) {
+        if ((long long)A.nCol * 8 <= 64LL << 20) return B200SPMV_OK;     // x fits in L2 next to the matrix stream
+        nb = (int)(((long long)A.nCol * 8 + COLBLOCK_SLICE_BYTES - 1) / COLBLOCK_SLICE_BYTES);
+        if (nb > COLBLOCK_MAX) nb = COLBLOCK_MAX;
+        const int B = (A.nCol + nb - 1) / nb;
+        DevBuf<unsigned long long> stats;
+        B2_TRY(stats.alloc(2));
+        B2_CUDA(cudaMemsetAsync(stats.p, 0, stats.bytes(), s));
+        colblock_spread_kernel<<<ceil_div(A.nRow, 256), 256, 0, s>>>(row_ptr, A.col, A.nRow, B, stats.p);
+        B2_KERNEL_CHECK();
+        unsigned long long st[2] = {0, 0};
+        B2_CUDA(cudaMemcpyAsync(st, stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        // rows that each live in one block (stencils, banded matrices) already reuse x through L1 / L2
+        if ((double)st[0] < 1.5 * (double)st[1]) return B200SPMV_OK;
+    }
+    b200spmv_options o{};
+    o.segment_width = 1;
+    o.n_block = nb;
+    std::unique_ptr<CrsColBlocks> e(new CrsColBlocks(o));
+    e->css.gather_bound = true;
+    B2_TRY(e->css.convert(A, s));
+    *out = std::move(e);
+    return B200SPMV_OK;
+}
 
 }  // namespace b2

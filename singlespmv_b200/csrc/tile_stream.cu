@@ -1,6 +1,7 @@
 // tile_stream.cu -- kernels of the tile-stream multiply (see tile_stream.cuh).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "tile_stream.cuh"
 
@@ -47,7 +48,11 @@ __device__ __forceinline__ double ld_val1(const float *p, uint64_t pol)
     return (double)r;
 }
 
-template <typename VT, int TH>
+// TMA = true: the tile's col / val slices are brought into shared memory by two 1-D bulk copies issued by one thread
+// (cp.async.bulk, SASS UBLKCP) instead of through every thread's load pipeline.  An SM sustains about one L1-missing
+// sector per clock (profiles/r2_gather_ceiling.md); on gather-bound matrices the x gathers need all of that, so the
+// 12 B/nnz matrix stream is taken off it.  The products overwrite the staged values in place.
+template <typename VT, int TH, bool TMA>
 __global__ void __launch_bounds__(TH)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const int *__restrict__ tile_row,
@@ -56,6 +61,9 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
 {
     constexpr int TILE = TH * TS_IPT;
     __shared__ __align__(16) double prod[TILE];
+    __shared__ __align__(16) int scol[TMA ? TILE : 4];
+    __shared__ __align__(16) VT sval32[(TMA && sizeof(VT) == 4) ? TILE : 4];   // fp32 values cannot share prod's slots
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int long_row[TILE / TS_LONG + 2];
     __shared__ int n_long;
 
@@ -68,7 +76,45 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     if (tid == 0) n_long = 0;
 
     // ---- phase 1: stream the tile, gather x, park products in shared memory
-    if (t1 - t0 == TILE && vec_ok) {
+    if (TMA) {
+        VT *sval = sizeof(VT) == 8 ? reinterpret_cast<VT *>(prod) : sval32;
+        const int n = t1 - t0;
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytesI = (uint32_t)((n * 4 + 15) & ~15), bytesV = (uint32_t)((n * (int)sizeof(VT) + 15) & ~15);
+            mbar_expect_tx(&bar, bytesI + bytesV);
+            tma_load_1d(scol, col + t0, bytesI, &bar, pol_stream);
+            tma_load_1d(sval, val + t0, bytesV, &bar, pol_stream);
+        }
+        mbar_wait(&bar, 0);
+        if (n == TILE) {
+            double xs[TS_IPT];
+            int4 c[TS_IPT / 4];
+#pragma unroll
+            for (int k = 0; k < TS_IPT / 4; k++) c[k] = *reinterpret_cast<const int4 *>(scol + 4 * (tid + k * TH));
+#pragma unroll
+            for (int k = 0; k < TS_IPT / 4; k++) {
+                xs[4 * k + 0] = ld_x(x + c[k].x, pol_x);
+                xs[4 * k + 1] = ld_x(x + c[k].y, pol_x);
+                xs[4 * k + 2] = ld_x(x + c[k].z, pol_x);
+                xs[4 * k + 3] = ld_x(x + c[k].w, pol_x);
+            }
+#pragma unroll
+            for (int k = 0; k < TS_IPT / 4; k++) {
+                const int o = 4 * (tid + k * TH);
+                const double v0 = (double)sval[o], v1 = (double)sval[o + 1], v2 = (double)sval[o + 2], v3 = (double)sval[o + 3];
+                double2 *dst = reinterpret_cast<double2 *>(prod + o);
+                dst[0] = make_double2(__dmul_rn(v0, xs[4 * k]), __dmul_rn(v1, xs[4 * k + 1]));
+                dst[1] = make_double2(__dmul_rn(v2, xs[4 * k + 2]), __dmul_rn(v3, xs[4 * k + 3]));
+            }
+        } else {
+            for (int i = tid; i < n; i += TH) {
+                const double v = (double)sval[i];
+                prod[i] = __dmul_rn(v, ld_x(x + scol[i], pol_x));
+            }
+        }
+    } else if (t1 - t0 == TILE && vec_ok) {
         int4 c[TS_IPT / 4];
         double2 v[TS_IPT / 2];
 #pragma unroll
@@ -113,9 +159,9 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
             long_row[atomicAdd(&n_long, 1)] = r;
             continue;
         }
-        double acc = 0.0;
+        double acc = accumulate == CS_CONTINUE ? y[r] : 0.0;          // CONTINUE: the running sum of the earlier column blocks
         for (int j = b; j < e; j++) acc = __dadd_rn(acc, prod[j - t0]);
-        y[r] = accumulate ? __dadd_rn(y[r], acc) : acc;
+        y[r] = accumulate == CS_ADD ? __dadd_rn(y[r], acc) : acc;
     }
     if (tid == 0 && cin_end > t0) {
         const int rc = r_lo - 1;
@@ -167,9 +213,9 @@ __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__
     const int b = row_ptr[rc];
     if (t != b / tile + 1) return;
     if (e - b <= TS_LONG) {
-        double acc = 0.0;
+        double acc = accumulate == CS_CONTINUE ? y[rc] : 0.0;
         for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn((double)val[j], x[col[j]]));
-        y[rc] = accumulate ? __dadd_rn(y[rc], acc) : acc;
+        y[rc] = accumulate == CS_ADD ? __dadd_rn(y[rc], acc) : acc;
     } else {
         const int last = (e - 1) / tile;
         double sum = 0.0;
@@ -188,7 +234,9 @@ int TileStream::build(const int *row_ptr_d, const int *col_d, const void *val_d,
     nRow = nRow_;
     nnz = nnz_;
     static const int env_threads = getenv("B200SPMV_TS_THREADS") ? atoi(getenv("B200SPMV_TS_THREADS")) : 256;
-    threads = (env_threads == 64 || env_threads == 128 || env_threads == 512) ? env_threads : 256;
+    threads = (env_threads == 128 || env_threads == 512) ? env_threads : 256;
+    static const char *env_load = getenv("B200SPMV_TS_LOAD");           // "ldg" / "tma": how the tile's slices are read
+    if (env_load) tma = !strcmp(env_load, "tma");
     tile = threads * TS_IPT;
     nTiles = ceil_div(nnz, tile);
     B2_TRY(tile_row.alloc((size_t)nTiles + 1));
@@ -199,7 +247,7 @@ int TileStream::build(const int *row_ptr_d, const int *col_d, const void *val_d,
     return B200SPMV_OK;
 }
 
-int TileStream::run_rows(const double *x, double *y, bool accumulate, int rb, int re, cudaStream_t s)
+int TileStream::run_rows(const double *x, double *y, int accumulate, int rb, int re, cudaStream_t s)
 {
     if (rb < 0 || re > nRow || rb > re) {
         set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow);
@@ -242,7 +290,7 @@ int TileStream::prepare(int rb, int re)
     return B200SPMV_OK;
 }
 
-int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo,
+int TileStream::run(const double *x, double *y, int accumulate, int rowLo, int rowHi, int tileLo,
                     int tileHi, cudaStream_t s) const
 {
     if (rowHi <= rowLo) return B200SPMV_OK;
@@ -251,23 +299,33 @@ int TileStream::run(const double *x, double *y, bool accumulate, int rowLo, int 
         return B200SPMV_OK;
     }
     const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
-    const int nT = tileHi - tileLo, acc = accumulate ? 1 : 0;
+    const int nT = tileHi - tileLo, acc = accumulate;
     const bool fix = nT > 1 || tileLo > 0;
+    // bulk copies need 16-byte aligned slices and may read up to 15 bytes past the last entry (callers keep CS_SLACK)
+    const bool use_tma = tma && vec_ok;
+    static bool carveout_set = false;
+    if (use_tma && !carveout_set) {       // 8 resident CTAs x 24.7 KB: ask for the large shared-memory split once
+        carveout_set = true;
+        cudaFuncSetAttribute(tile_stream_kernel<double, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(tile_stream_kernel<float, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(tile_stream_kernel<double, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(tile_stream_kernel<float, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
+    }
 #define TS_LAUNCH(VT, TH, v)                                                                                                      \
     do {                                                                                                                          \
-        tile_stream_kernel<VT, TH><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
+        if (use_tma && TH <= 256) tile_stream_kernel<VT, (TH <= 256 ? TH : 256), true><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
+        else tile_stream_kernel<VT, TH, false><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
         if (fix) tile_fixup_kernel<VT><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc, tile); \
     } while (0)
     if (f32) {
         const float *v = static_cast<const float *>(val);
-        if (threads == 64) TS_LAUNCH(float, 64, v);
-        else if (threads == 128) TS_LAUNCH(float, 128, v);
+        if (threads == 128) TS_LAUNCH(float, 128, v);
         else if (threads == 512) TS_LAUNCH(float, 512, v);
         else TS_LAUNCH(float, 256, v);
     } else {
         const double *v = static_cast<const double *>(val);
-        if (threads == 64) TS_LAUNCH(double, 64, v);
-        else if (threads == 128) TS_LAUNCH(double, 128, v);
+        if (threads == 128) TS_LAUNCH(double, 128, v);
         else if (threads == 512) TS_LAUNCH(double, 512, v);
         else TS_LAUNCH(double, 256, v);
     }

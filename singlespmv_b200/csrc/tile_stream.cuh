@@ -44,31 +44,29 @@ struct TileStream {
     // owned
     int nTiles = 0;
     int threads = TS_THREADS, tile = TS_TILE;   // CTA width and entries per tile of this instance
+    bool tma = false;               // tile slices arrive by TMA bulk copy instead of through the threads' loads
     DevBuf<int> tile_row;           // [nTiles+1]: first row whose first entry is >= tile start
     DevBuf<double> carry;           // [nTiles]
 
     int build(const int *row_ptr_d, const int *col_d, const void *val_d, bool val_is_f32, int nRow_, int nnz_,
               cudaStream_t s);
     // y[rowLo..rowHi) = (accumulate ? y : 0) + A x, restricted to tiles [tileLo, tileHi)
-    int run(const double *x, double *y, bool accumulate, int rowLo, int rowHi, int tileLo, int tileHi,
+    // accumulate: CS_OVERWRITE / CS_CONTINUE / CS_ADD (common.cuh)
+    int run(const double *x, double *y, int accumulate, int rowLo, int rowHi, int tileLo, int tileHi,
             cudaStream_t s) const;
-    int run_all(const double *x, double *y, bool accumulate, cudaStream_t s) const
+    int run_all(const double *x, double *y, int accumulate, cudaStream_t s) const
     {
         return run(x, y, accumulate, 0, nRow, 0, nTiles, s);
     }
     // rows [rb, re) only: looks up (and caches) the tiles that hold their entries
-    int run_rows(const double *x, double *y, bool accumulate, int rb, int re, cudaStream_t s);
+    int run_rows(const double *x, double *y, int accumulate, int rb, int re, cudaStream_t s);
     int prepare(int rb, int re);
     size_t meta_bytes() const { return tile_row.bytes(); }
     std::map<std::pair<int, int>, std::pair<int, int>> range_cache;
 };
 
-// short-row alternatives to the tile-stream (crs.cu), one launch, every row bit-exact: the TMA-fed row-chunk stream
-// (default; idx and val need SHORT_ROW_SLACK entries of allocation slack) and the warp-per-32-rows row-block stream
-constexpr int SHORT_ROW_SLACK = 8;
-// kernel: 0 = default (row-chunk stream), 2 = row-block stream, 3 = row-chunk stream  (options.crs_path)
-int short_row_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
-                   double *y, int kernel, cudaStream_t s);
+// round 1's short-row alternative to the tile-stream (crs.cu): warp-per-32-rows stream, no tiles, one launch.  Kept
+// as options.crs_path = 2 for A/B runs; the default short-row kernel is the TMA-fed row-chunk stream (chunk_stream.cuh)
 int rowblock_spmv(const int *ptr, const int *idx, const void *val, bool f32, int maxLen, int rb, int re, const double *x,
                   double *y, cudaStream_t s);
 bool rowblock_applies(int maxLen, long long nnz);

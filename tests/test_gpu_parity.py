@@ -172,7 +172,7 @@ def test_crs_paths_agree(sp, oracle):
                 assert A_auto.scalar("short_row_path") == 1 and A_tile.scalar("short_row_path") == 0
                 assert A_auto.scalar("launches") == 1 and A_tile.scalar("launches") == 2
             assert np.array_equal(y_auto, y_ref) and np.array_equal(y_tile, y_ref)
-    # longer rows: the row-block stream does not apply
+    # longer rows: the short-row kernels do not apply
     nr, nc, row, col, val = oracle.stencil("box3d27", 9)
     A_opt, _ = run_host(sp, "crs", nr, nc, row, col, val, np.ones(nc))
     assert A_opt.scalar("short_row_path") == 0 and A_opt.scalar("maxLength") == 27
@@ -828,7 +828,7 @@ def test_multiply_rows_in_cuda_graph_after_prepare(sp, oracle):
     nr, nc, row, col, val = oracle.stencil("box3d27", 14)
     x = oracle.reference_vectors(nc, nr)[0]
     y_ref = oracle.crs_result(nr, row, col, val, x)
-    A_opt = sp.SpMatOpt("crs").convert_host(sp.SpMat(nr, nc, row, col, val))
+    A_opt = sp.SpMatOpt("crs", crs_path=1).convert_host(sp.SpMat(nr, nc, row, col, val))
     assert A_opt.scalar("short_row_path") == 0
     xd = torch.from_numpy(x).cuda()
     yd = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
@@ -857,3 +857,57 @@ def test_ss_css_profile_phases(sp, oracle):
         assert A_opt.scalar("MulTime_ns") > 0 and A_opt.scalar("SumTime_ns") > 0
         B_opt, y2 = run_host(sp, fmt, nr, nc, row, col, val, x, ss_faithful=1, **opt)
         assert np.array_equal(y, y2) and B_opt.scalar("MulTime_ns") == 0
+
+
+@pytest.mark.parametrize("fmt", ["ell", "jds", "ss"])
+def test_column_blocked_layout_bit_exact(sp, oracle, fmt):
+    """options.col_blocks: the row-wise formats multiplied column block by column block (colblocks.cuh), each row's
+    running sum continued from block to block -> same bits as the reference CRS result for any block count, empty rows
+    included; the reference arrays the format exports are untouched."""
+    rng = np.random.default_rng(31)
+    mats = []
+    nRow, nCol = 3001, 2500
+    row, col, val = _short_row_matrix(rng, nRow, nCol, 24)
+    mats.append((nRow, nCol, row, col, val, rng.random(nCol)))
+    nr, nc, r_, c_, v_ = oracle.uniform(1, 4096, 4096, 32)
+    mats.append((nr, nc, r_, c_, v_, oracle.reference_vectors(nc, nr)[0]))
+    nr, nc, r_, c_, v_ = oracle.stencil("lap2d5", 50)
+    mats.append((nr, nc, r_, c_, v_, oracle.reference_vectors(nc, nr)[0]))
+    for nRow, nCol, row, col, val, x in mats:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        base_opt, y0 = run_host(sp, fmt, nRow, nCol, row, col, val, x, col_blocks=-1)
+        assert base_opt.scalar("col_blocks") == 0 and np.array_equal(y0, y_ref)
+        for nb in (1, 2, 3, 7):
+            A_opt, y = run_host(sp, fmt, nRow, nCol, row, col, val, x, col_blocks=nb)
+            assert A_opt.scalar("col_blocks") >= 1 and A_opt.scalar("launches") >= A_opt.scalar("col_blocks")
+            assert np.array_equal(y, y_ref), (fmt, nb)
+            assert A_opt.scalar("alg_bytes") == base_opt.scalar("alg_bytes")
+        auto_opt, _ = run_host(sp, fmt, nRow, nCol, row, col, val, x)
+        assert auto_opt.scalar("col_blocks") == 0             # x fits in L2: the decision leaves small matrices alone
+
+
+def test_column_blocked_long_rows_within_tolerance(sp, oracle, all_cases):
+    """Rows with more than 64 entries in one column block are reduced by a warp: within the 1e-12 tolerance; every
+    other row stays bit-identical."""
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        if nCol < 4:
+            continue
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        A_opt, y = run_host(sp, "jds", nRow, nCol, row, col, val, x, col_blocks=2)
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        short = np.diff(np.searchsorted(row, np.arange(nRow + 1))) <= 64
+        assert np.array_equal(y[short], y_ref[short]), name
+
+
+@pytest.mark.parametrize("kind,n,maxlen", [("box3d27", 14, 27), ("lap3d7", 20, 7)])
+def test_css_blocks_on_row_chunk_stream(sp, oracle, kind, n, maxlen):
+    """CSS column blocks with short rows go through the row-chunk stream (block sums ADDED to y, src/opt_css.cpp:298);
+    result within the tolerance of the reference CRS result and equal to the tile-stream path's association."""
+    nr, nc, row, col, val = oracle.stencil(kind, n)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    for nb in (1, 2, 4):
+        A_opt, y = run_host(sp, "css", nr, nc, row, col, val, x, n_block=nb, segment_width=4)
+        assert_y(y, y_ref, row, col, val, x, nr)
+        if nb == 1:
+            assert np.array_equal(y, y_ref)

@@ -13,7 +13,7 @@ from conftest import load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "singlespmv_b200", "plugin", "bin")
-FORMATS = ["crs", "coo", "ell", "jds", "dia", "ss", "css", "csr5"]
+FORMATS = ["crs", "coo", "ell", "jds", "dia", "ss", "css", "csr5", "hyb"]
 
 
 @pytest.fixture(scope="module")
@@ -95,3 +95,22 @@ def test_driver_synth_shape(built):
     assert r.returncode == 0, r.stderr[-2000:]
     kv = parse_report(r.stdout)
     assert int(kv["nRow"]) == 24 ** 3 and int(kv["nNnz"]) == (3 * 24 - 2) ** 3 and kv["VectorResidency"] == "device"
+
+
+@pytest.mark.gpu
+def test_driver_report_keys_of_the_reference(built):
+    """Keys the reference's report carries and log/format consumers read (src/main.cpp:155-174,200-206): nThread for
+    every format; nStep + StepCount-xx for SS; MulPerf / SumPerf for the -DPROFILING builds of SS and CSS."""
+    env = dict(os.environ, SPMV_MIN_SECONDS="0.02", SPMV_NTRY="2")
+    r = subprocess.run([os.path.join(built, "spmv_b200_ss_dev"), "synth:lap2d5:64"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    kv = parse_report(r.stdout)
+    assert kv["nThread"] == "1" and kv["nGPU"] == "1"
+    n = int(kv["nStep"])
+    assert n >= 1 and all(("StepCount-%02d" % i) in kv for i in range(n))
+    assert sum(int(kv["StepCount-%02d" % i]) for i in range(n)) > 0
+    for exe, keys in (("spmv_b200_ss_prof", ("MulPerf", "SumPerf")), ("spmv_b200_css_prof", ("MulPerf(GFLOPS)", "SumPerf(GFLOPS)"))):
+        r = subprocess.run([os.path.join(built, exe), "synth:lap2d5:64"], capture_output=True, text=True, timeout=120, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        kv = parse_report(r.stdout)
+        assert all(float(kv[k]) > 0 for k in keys), kv
