@@ -40,16 +40,16 @@ sys.path.insert(0, ROOT)
 L2_BYTES = 126 * 1024 * 1024
 
 WORKLOADS = {
-    "c1": dict(kind="lap2d5", p0=1024, p1=0, seed=1, fmt="crs", formats=["crs", "dia", "ell"],
+    "c1": dict(kind="lap2d5", p0=1024, p1=0, seed=1, fmt="crs", formats=["crs", "dia", "ell"], f32=["crs"],
                name="CRS fp64, 2-D 5-point Laplacian 1024x1024 (1,048,576 rows, 5,238,784 nnz)"),
-    "c2": dict(kind="uniform", p0=1 << 24, p1=32, seed=1, fmt="ell", formats=["ell", "ss", "jds", "css"],
+    "c2": dict(kind="uniform", p0=1 << 24, p1=32, seed=1, fmt="ell", formats=["ell", "ss", "jds", "css"], f32=["ell", "crs"],
                fmt_opts={"css": dict(n_block=3)},
                name="sliced-ELL / SS / JDS fp64, uniform random 16,777,216 rows x 32 nnz/row (536,870,912 nnz)"),
-    "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="csr5", formats=["csr5", "crs"], cusparse=True,
+    "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="csr5", formats=["csr5", "crs"], cusparse=True, f32=["crs"],
                name="CSR5-style and adaptive CRS fp64, R-MAT scale 23, 2^28 edge draws (duplicates removed)"),
-    "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia", formats=["dia", "ell", "crs"],
+    "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia", formats=["dia", "ell", "crs"], f32=["ell"],
                name="DIA fp64, 3-D 27-point stencil 256^3 (16,777,216 rows, 449,455,096 nnz)"),
-    "c5": dict(kind="lap3d7", p0=512, p1=0, seed=1, fmt="crs", cusparse=True,
+    "c5": dict(kind="lap3d7", p0=512, p1=0, seed=1, fmt="crs", cusparse=True, f32=["crs", "ell"],
                formats=["crs", "dia", "ell", "jds", "ss", "css", "csr5", "coo"],
                name="row-partitioned CRS fp64, 3-D 7-point Laplacian 512^3 (134,217,728 rows, 937,951,232 nnz)"),
 }
@@ -375,17 +375,19 @@ class Timer:
             return None
 
 
-def parity_of(y, y_ref, mag):
-    """Per-row comparison with the reference CRS result (SURVEY.md 8d tolerance: rel <= tol OR |dy| <= tol * sum |a x|)."""
+def parity_of(y, y_ref, mag, tol=1e-12):
+    """Per-row comparison with the reference CRS result (SURVEY.md 8d tolerance: rel <= tol OR |dy| <= tol * sum |a x|;
+    tol = 1e-12 for fp64, 1e-5 for the fp32 variant)."""
     import numpy as np
+    y = y.astype(np.float64)
     err = np.abs(y - y_ref)
     with np.errstate(divide="ignore", invalid="ignore"):
         rel = np.where(y_ref != 0, err / np.abs(y_ref), np.where(err == 0, 0.0, np.inf))
         relmag = np.where(mag != 0, err / mag, np.where(err == 0, 0.0, np.inf))
-    ok = (rel <= 1e-12) | (relmag <= 1e-12)
+    ok = (rel <= tol) | (relmag <= tol)
     return {"rows": int(len(y)), "max_rel": float(rel.max()) if len(y) else 0.0,
             "max_rel_to_mag": float(relmag.max()) if len(y) else 0.0,
-            "bit_identical": bool(np.array_equal(y, y_ref)), "within_1e-12": bool(ok.all())}
+            "bit_identical": bool(np.array_equal(y, y_ref)), "within_%g" % tol: bool(ok.all())}
 
 
 def cpu_sample(sp, wl, x_h):
@@ -414,9 +416,16 @@ def run_case(sp, torch, timer, wl_key, wl, fmt, options, coo, x_d, y_d, sptr, st
     t_conv = time.perf_counter() - t0
     alg_bytes = A.scalar("alg_bytes")
     cold = alg_bytes < 2 * L2_BYTES
+    f32 = bool(options.get("precision"))
+    if f32:                                  # fp32 variant: float x and y (options.precision)
+        x_d = x_d.float()
+        y_d = torch.empty(y_d.shape, dtype=torch.float32, device="cuda")
 
     def step(s=None):
-        A.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr if s is None else s)
+        if f32:
+            A.multiply_f32(x_d.data_ptr(), y_d.data_ptr(), sptr if s is None else s)
+        else:
+            A.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr if s is None else s)
     y_d.fill_(float("nan"))
     ms = timer.run(step, steps, warmup, cold)
     nnz = A.nNnz
@@ -435,7 +444,9 @@ def run_case(sp, torch, timer, wl_key, wl, fmt, options, coo, x_d, y_d, sptr, st
         _, rows, y_ref, mag = sample
         step()
         torch.cuda.synchronize()
-        e["parity"] = parity_of(y_d[:rows].cpu().numpy(), y_ref, mag)
+        e["parity"] = parity_of(y_d[:rows].cpu().numpy(), y_ref, mag, 1e-5 if f32 else 1e-12)
+    if f32:
+        e["dtype"] = "f32 values and vectors, %s sums" % ("f32" if options["precision"] == 1 else "f64")
     return e, A
 
 
@@ -526,26 +537,35 @@ def run_single(args, wl_key, only_format):
     # e2e: the reference-facing call SpMV(A_opt, x_opt, y) with HOST vectors, exactly as the C++ plugin issues it
     # (singlespmv_b200/plugin/opt_b200.cpp): x and y are ordinary (pageable) host arrays that the plugin page-locks once
     # -- x in OptimizeProblem, y on the first SpMV -- then every step is H2D x, multiply, D2H y inside the timed region
-    xh = x_h.copy()
-    yh = np.empty(nRow, np.float64)
+    f32 = bool(options.get("precision"))
+    xh = x_h.astype(np.float32) if f32 else x_h.copy()
+    yh = np.empty(nRow, np.float32 if f32 else np.float64)
+    host_call = A.multiply_host_f32 if f32 else A.multiply_host
     pinned = sp.host_register(xh) and sp.host_register(yh)
     for _ in range(min(args.warmup, 3)):
-        A.multiply_host(xh, yh)
+        host_call(xh, yh)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        A.multiply_host(xh, yh)
+        host_call(xh, yh)
     e2e_s = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
-    A.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr)
-    torch.cuda.synchronize()
-    assert torch.equal(torch.from_numpy(yh), y_d.cpu()), "host-semantics and device-resident results differ"
+    if f32:
+        x32, y32 = x_d.float(), torch.empty(nRow, dtype=torch.float32, device="cuda")
+        A.multiply_f32(x32.data_ptr(), y32.data_ptr(), sptr)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.from_numpy(yh), y32.cpu()), "host-semantics and device-resident results differ"
+        del x32, y32
+    else:
+        A.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.from_numpy(yh), y_d.cpu()), "host-semantics and device-resident results differ"
     sp.host_unregister(xh)
     sp.host_unregister(yh)
 
     dom_launches = A.scalar("nBlock") if fmt == "css" else 1
     line = {"metric": "SpMV GFLOP/s", "value": head["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32" if f32 else "f64", "data": "synthetic",
             "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "options": head["options"], "nRow": nRow,
                        "nCol": nCol, "nnz": nnz, "x": "srand(3) rand()/RAND_MAX (src/main.cpp:18,31)",
                        "l2": "flushed between steps (512 MiB write)" if head["l2"].startswith("flushed")
@@ -559,7 +579,7 @@ def run_single(args, wl_key, only_format):
                          "note": "achieved = alg_bytes_per_launch / avg_launch_ms (CUDA events over the timed region); "
                                  "traffic = ncu dram read+write of one launch (profiles/)"},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": 8 * nCol, "d2h_bytes_per_step": 8 * nRow,
+                    "h2d_bytes_per_step": (4 if f32 else 8) * nCol, "d2h_bytes_per_step": (4 if f32 else 8) * nRow,
                     "host_buffers": "numpy arrays page-locked once by the plugin layer (cudaHostRegister), as "
                                     "plugin/opt_b200.cpp does for the driver's x and y" if pinned else "pageable numpy arrays"},
             "gpu_launches": head["launches_per_step"] * args.steps, "clocks": clocks}
@@ -615,6 +635,15 @@ def run_single(args, wl_key, only_format):
                             e2 = {"format": f2, "error": str(err)}
                     e2.pop("format", None)
                     entry["formats"][f2] = e2
+                for f2 in w.get("f32", []):                # the fp32 variant (options.precision = 1), tolerance 1e-5
+                    A.destroy()
+                    try:
+                        e2, A = run_case(sp, torch, timer, key, w, f2, dict(precision=1), coo, x_d, y_d, sptr, steps2, warm2,
+                                         peak, args.mini, sample)
+                    except sp.B200SpmvError as err:
+                        e2 = {"format": f2, "error": str(err)}
+                    e2.pop("format", None)
+                    entry["formats"][f2 + "_f32"] = e2
                 if w.get("cusparse"):
                     A.destroy()
                     A = sp.SpMatOpt("crs").convert_device(coo)      # y_d must hold a full result for the difference check
@@ -653,10 +682,11 @@ def main():
     ap.add_argument("--n-block", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=0)
     ap.add_argument("--value-f32", action="store_true", help="CRS: fp32 storage of the matrix values, fp64 arithmetic")
+    ap.add_argument("--precision", type=int, default=0, help="CRS / ELL: 1 = fp32 values, vectors and sums, 2 = fp32 with fp64 sums")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.options = dict(segment_width=args.segment_width, n_block=args.n_block, csr5_sigma=args.sigma,
-                        value_f32=1 if args.value_f32 else 0)
+                        value_f32=1 if args.value_f32 else 0, precision=args.precision)
     wl_key = args.workload or HEADLINE
     if args.configs is None:
         args.configs = "none" if (args.workload or args.format) else "all"

@@ -86,8 +86,12 @@ typedef struct {
                             blocks), n > 0 = force n column blocks, -1 = never.  The reference arrays (exports) and y
                             are the same either way: every row is still summed in ascending column order (rows of more
                             than 64 entries per block: within the 1e-12 tolerance) */
+    int precision;       /* CRS / ELL: 0 = fp64 (the reference); 1 = fp32: matrix values rounded once to fp32 at conversion,
+                            x and y are float arrays, products and sums in fp32; 2 = the same storage and vectors with
+                            fp64 products and sums.  Multiply with b200spmv_multiply_f32 / _host_f32; tolerance 1e-5
+                            against the reference's (fp64) CRS result.  Halves the bytes of every array but the indices */
     int hyb_k;           /* HYB: width of the ELL part; 0 = the largest width that max(4096, nRow/3) rows still fill */
-    int reserved[7];
+    int reserved[6];
 } b200spmv_options;
 
 /* ---- library ---- */
@@ -119,6 +123,10 @@ B200SPMV_API int b200spmv_multiply(b200spmv_matrix *m, const double *x_d, double
 /* Host semantics (what SpMV(A_opt, x_opt, y) means to the reference's driver): copies x H2D,
  * multiplies, copies y D2H, synchronises -- like src/opt_cusparse.cpp:72-82. */
 B200SPMV_API int b200spmv_multiply_host(b200spmv_matrix *m, const double *x_h, double *y_h);
+/* fp32 variant (options.precision = 1 or 2; src/param.h has no value-type switch, the CSR5 benchmark the reference
+ * vendors does: CSR5_cuda/Makefile:4 VALUE_TYPE).  The handle must have been created with that precision. */
+B200SPMV_API int b200spmv_multiply_f32(b200spmv_matrix *m, const float *x_d, float *y_d, void *stream);
+B200SPMV_API int b200spmv_multiply_host_f32(b200spmv_matrix *m, const float *x_h, float *y_h);
 /* Rows [rowBegin,rowEnd) only (CRS, SS, CSS, ELL, DIA; others return B200SPMV_ERR_UNSUPPORTED): used by
  * the row-partitioned multi-GPU path to overlap the interior block with the halo exchange, and by
  * b200spmv_multiply_host to overlap the D2H copy of finished rows with the rest of the multiply. */

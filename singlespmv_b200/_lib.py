@@ -21,7 +21,7 @@ class B200SpmvError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("segment_width", C.c_int), ("n_block", C.c_int), ("csr5_sigma", C.c_int),
-                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("hyb_k", C.c_int), ("reserved", C.c_int * 7)]
+                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("precision", C.c_int), ("hyb_k", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class Stats(C.Structure):
@@ -53,6 +53,8 @@ def _load():
     lib.b200spmv_jds_set_perm_host.argtypes = [vp, vp, ip]
     lib.b200spmv_multiply.argtypes = [vp, vp, vp, vp]
     lib.b200spmv_multiply_host.argtypes = [vp, vp, vp]
+    lib.b200spmv_multiply_f32.argtypes = [vp, vp, vp, vp]
+    lib.b200spmv_multiply_host_f32.argtypes = [vp, vp, vp]
     lib.b200spmv_multiply_rows.argtypes = [vp, ip, ip, vp, vp, vp]
     lib.b200spmv_prepare_rows.argtypes = [vp, ip, ip]
     lib.b200spmv_rows_col_extent.argtypes = [vp, ip, ip, C.POINTER(ip), C.POINTER(ip)]

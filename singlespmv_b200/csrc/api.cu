@@ -30,6 +30,7 @@ struct b200spmv_matrix {
     long long piece_c0[B200SPMV_HOST_SLICES + 1] = {};
     // staging for host-semantics multiply
     DevBuf<double> x_stage, y_stage;
+    DevBuf<float> x_stage32, y_stage32;
     cudaStream_t stream = nullptr, copy_stream = nullptr, in_stream = nullptr;
     cudaEvent_t chunk_done[B200SPMV_HOST_CHUNKS] = {};
     cudaEvent_t slice_in[B200SPMV_HOST_SLICES] = {};
@@ -125,6 +126,11 @@ int b200spmv_create(int format, const b200spmv_options *opts, b200spmv_matrix **
         set_error("create: value_f32 is implemented for the CRS format only");
         return B200SPMV_ERR_UNSUPPORTED;
     }
+    if (o.precision < 0 || o.precision > 2) { set_error("create: precision=%d (0 fp64, 1 fp32, 2 fp32 with fp64 sums)", o.precision); return B200SPMV_ERR_INVALID; }
+    if (o.precision && format != B200SPMV_CRS && format != B200SPMV_ELL) {
+        set_error("create: the fp32 variant exists for the CRS and ELL formats");
+        return B200SPMV_ERR_UNSUPPORTED;
+    }
     Format *f = make_format(format, o);
     if (!f) {
         set_error("create: unknown format %d", format);
@@ -203,6 +209,25 @@ int b200spmv_multiply(b200spmv_matrix *m, const double *x_d, double *y_d, void *
 {
     B2_TRY(check_ready(m, x_d, y_d));
     return m->impl->multiply(x_d, y_d, (cudaStream_t)stream);
+}
+
+int b200spmv_multiply_f32(b200spmv_matrix *m, const float *x_d, float *y_d, void *stream)
+{
+    B2_TRY(check_ready(m, x_d, y_d));
+    return m->impl->multiply_f32(x_d, y_d, (cudaStream_t)stream);
+}
+
+int b200spmv_multiply_host_f32(b200spmv_matrix *m, const float *x_h, float *y_h)
+{
+    B2_TRY(check_ready(m, x_h, y_h));
+    Format *f = m->impl.get();
+    if (m->x_stage32.n != (size_t)f->nCol) B2_TRY(m->x_stage32.alloc((size_t)f->nCol));
+    if (m->y_stage32.n != (size_t)f->nRow) B2_TRY(m->y_stage32.alloc((size_t)f->nRow));
+    B2_CUDA(cudaMemcpyAsync(m->x_stage32.p, x_h, sizeof(float) * (size_t)f->nCol, cudaMemcpyHostToDevice, nullptr));
+    B2_TRY(f->multiply_f32(m->x_stage32.p, m->y_stage32.p, nullptr));
+    B2_CUDA(cudaMemcpyAsync(y_h, m->y_stage32.p, sizeof(float) * (size_t)f->nRow, cudaMemcpyDeviceToHost, nullptr));
+    B2_CUDA(cudaStreamSynchronize(nullptr));
+    return B200SPMV_OK;
 }
 
 int b200spmv_multiply_rows(b200spmv_matrix *m, int rowBegin, int rowEnd, const double *x_d, double *y_d,

@@ -7,10 +7,11 @@
 
 namespace b2 {
 
-template <typename VT, int MAXL, int TH, bool ACC>
+// VT = stored value type, XT = type of x and y, AT = type the row sums are accumulated in
+template <typename VT, typename XT, typename AT, int MAXL, int TH, bool ACC>
 __global__ void __launch_bounds__(TH)
 chunk_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, const VT *__restrict__ val,
-                    const double *__restrict__ x, double *__restrict__ y, int rowBegin, int rowEnd, int chunk0,
+                    const XT *__restrict__ x, XT *__restrict__ y, int rowBegin, int rowEnd, int chunk0,
                     int nChunks, int capI, int capV, int S, int acc_mode)
 {
     extern __shared__ __align__(128) unsigned char cs_smem[];
@@ -72,19 +73,19 @@ chunk_stream_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, co
             pn = ptr[rn];
             qn = ptr[rn + 1];
         }
-        const double y0 = (ACC && valid) ? y[r] : 0.0;
+        const AT y0 = (ACC && valid) ? (AT)y[r] : (AT)0;
         mbar_wait(&bar[s], (uint32_t)(k / S) & 1u);
         const int io = s * capI + (p - sbaseI[s]), vo = s * capV + (p - sbaseV[s]);
         const int len = q - p;
-        double acc = (ACC && acc_mode == CS_CONTINUE) ? y0 : 0.0;
-        double xs[MAXL];
+        AT acc = (ACC && acc_mode == CS_CONTINUE) ? y0 : (AT)0;
+        XT xs[MAXL];
 #pragma unroll
         for (int j = 0; j < MAXL; j++)
             if (j < len) xs[j] = ld_x(x + sidx[io + j], pol_x);
 #pragma unroll
         for (int j = 0; j < MAXL; j++)
-            if (j < len) acc = __dadd_rn(acc, __dmul_rn((double)sval[vo + j], xs[j]));
-        if (valid) y[r] = (ACC && acc_mode == CS_ADD) ? __dadd_rn(y0, acc) : acc;
+            if (j < len) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)sval[vo + j], (AT)xs[j]));
+        if (valid) y[r] = (XT)((ACC && acc_mode == CS_ADD) ? Arith<AT>::add(y0, acc) : acc);
         __syncthreads();                                       // every thread is done with stage s
         if (tid == 0 && cIssue < nChunks) issue(s, nb, ne);
         r = rn; p = pn; q = qn; valid = validn;
@@ -125,8 +126,8 @@ int ChunkStream::build(const int *ptr_d, const int *idx_d, const void *val_d, bo
     return B200SPMV_OK;
 }
 
-template <typename VT, int MAXL, int TH, bool ACC>
-static int cs_launch(const ChunkStream &c, const double *x, double *y, int rb, int re, int acc, cudaStream_t s)
+template <typename VT, typename XT, typename AT, int MAXL, int TH, bool ACC>
+static int cs_launch(const ChunkStream &c, const XT *x, XT *y, int rb, int re, int acc, cudaStream_t s)
 {
     constexpr int VA = 16 / (int)sizeof(VT);
     static const int env_s = getenv("B200SPMV_TMA_S") ? atoi(getenv("B200SPMV_TMA_S")) : 0;
@@ -134,7 +135,7 @@ static int cs_launch(const ChunkStream &c, const double *x, double *y, int rb, i
     const int S = (env_s >= 1 && env_s <= CS_MAXSTAGES) ? env_s : 2;
     const int capI = (c.cap + 8) & ~3, capV = (c.cap + 2 * VA) & ~(VA - 1);
     const size_t smem = (size_t)S * ((size_t)capI * 4 + (size_t)capV * sizeof(VT));
-    auto kern = chunk_stream_kernel<VT, MAXL, TH, ACC>;
+    auto kern = chunk_stream_kernel<VT, XT, AT, MAXL, TH, ACC>;
     static int sms = 0;
     static std::map<size_t, int> per_sm;                        // occupancy of THIS instantiation by shared-memory size
     if (!sms) {
@@ -158,25 +159,37 @@ static int cs_launch(const ChunkStream &c, const double *x, double *y, int rb, i
     return B200SPMV_OK;
 }
 
+template <typename VT, typename XT, typename AT>
+static int cs_dispatch(const ChunkStream &c, const XT *x, XT *y, int rb, int re, int acc, cudaStream_t s)
+{
+#define CS_GO(MAXL)                                                                                       \
+    do {                                                                                                  \
+        if (c.th == 512 && acc) return cs_launch<VT, XT, AT, MAXL, 512, true>(c, x, y, rb, re, acc, s);   \
+        if (c.th == 512) return cs_launch<VT, XT, AT, MAXL, 512, false>(c, x, y, rb, re, acc, s);         \
+        if (acc) return cs_launch<VT, XT, AT, MAXL, 256, true>(c, x, y, rb, re, acc, s);                  \
+        return cs_launch<VT, XT, AT, MAXL, 256, false>(c, x, y, rb, re, acc, s);                          \
+    } while (0)
+    if (c.maxLen <= 8) CS_GO(8);
+    else CS_GO(16);
+#undef CS_GO
+}
+
 int ChunkStream::run(const double *x, double *y, int rb, int re, int acc, cudaStream_t s) const
 {
     if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow); return B200SPMV_ERR_INVALID; }
     if (rb == re) return B200SPMV_OK;
-#define CS_GO(VT, MAXL)                                                                        \
-    do {                                                                                       \
-        if (th == 512 && acc) return cs_launch<VT, MAXL, 512, true>(*this, x, y, rb, re, acc, s);  \
-        if (th == 512) return cs_launch<VT, MAXL, 512, false>(*this, x, y, rb, re, acc, s);        \
-        if (acc) return cs_launch<VT, MAXL, 256, true>(*this, x, y, rb, re, acc, s);               \
-        return cs_launch<VT, MAXL, 256, false>(*this, x, y, rb, re, acc, s);                       \
-    } while (0)
-    if (f32) {
-        if (maxLen <= 8) CS_GO(float, 8);
-        else CS_GO(float, 16);
-    } else {
-        if (maxLen <= 8) CS_GO(double, 8);
-        else CS_GO(double, 16);
-    }
-#undef CS_GO
+    if (f32) return cs_dispatch<float, double, double>(*this, x, y, rb, re, acc, s);
+    return cs_dispatch<double, double, double>(*this, x, y, rb, re, acc, s);
+}
+
+// fp32 vectors (values must be stored as fp32): accumulation in fp32 or fp64
+int ChunkStream::run_f32(const float *x, float *y, int rb, int re, int acc, bool acc64, cudaStream_t s) const
+{
+    if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow); return B200SPMV_ERR_INVALID; }
+    if (!f32) { set_error("row-chunk stream: fp32 vectors need fp32 value storage"); return B200SPMV_ERR_STATE; }
+    if (rb == re) return B200SPMV_OK;
+    if (acc64) return cs_dispatch<float, float, double>(*this, x, y, rb, re, acc, s);
+    return cs_dispatch<float, float, float>(*this, x, y, rb, re, acc, s);
 }
 
 }  // namespace b2

@@ -32,6 +32,7 @@ struct ChunkStream {
     int build(const int *ptr_d, const int *idx_d, const void *val_d, bool val_is_f32, int nRow_, int nnz, int maxLen_,
               cudaStream_t s);
     int run(const double *x, double *y, int rb, int re, int acc, cudaStream_t s) const;
+    int run_f32(const float *x, float *y, int rb, int re, int acc, bool acc64, cudaStream_t s) const;
 };
 
 }  // namespace b2

@@ -87,6 +87,12 @@ struct Format {
     virtual ~Format() {}
     virtual int convert(const CooView &A, cudaStream_t s) = 0;
     virtual int multiply(const double *x, double *y, cudaStream_t s) = 0;
+    // options.precision = 1 / 2: fp32 matrix values and vectors (accumulation in fp32 / fp64)
+    virtual int multiply_f32(const float *, float *, cudaStream_t)
+    {
+        set_error("multiply_f32: this format has no fp32 variant (CRS, ELL and DIA do)");
+        return B200SPMV_ERR_UNSUPPORTED;
+    }
     virtual int multiply_rows(int, int, const double *, double *, cudaStream_t)
     {
         set_error("multiply_rows: this format does not support row ranges (CRS, SS, CSS, ELL, DIA do)");
@@ -239,6 +245,24 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
                  "[%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// Arithmetic of one precision: unfused multiply and add (the reference's g++ -O2 build does not contract, and a fixed
+// operation order keeps every kernel deterministic), and the x gather with the L2 evict-last hint.
+template <typename T> struct Arith;
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+__device__ __forceinline__ float ld_x(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
 }
 
 int xload_mode();   // value of B200SPMV_XLOAD (api.cu)

@@ -119,7 +119,8 @@ struct CrsFormat : Format {
     TileStream ts;
     ChunkStream cs;
     int path_opt;
-    explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0), path_opt(o.crs_path) {}
+    int prec;                             // options.precision: 0 fp64 vectors, 1 fp32 vectors + sums, 2 fp32 vectors, fp64 sums
+    explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0 || o.precision != 0), path_opt(o.crs_path), prec(o.precision) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -144,16 +145,23 @@ struct CrsFormat : Format {
         B2_TRY(cs.build(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, nRow, nnz, maxLen, s));
         // path: 1 = tile-stream always; 2 = round 1's row-block stream where it applies (longest row <= 16);
         // otherwise the TMA-fed row-chunk stream when the rows are short enough, else the tile-stream
-        use_rbs = path_opt == 2 && rowblock_applies(maxLen, nnz);
+        use_rbs = path_opt == 2 && !prec && rowblock_applies(maxLen, nnz);
         short_rows = path_opt != 1 && (use_rbs || cs.ok);
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
+    int multiply_f32(const float *x, float *y, cudaStream_t s) override
+    {
+        if (!prec) { set_error("multiply_f32: the handle was created with precision = 0 (fp64 vectors)"); return B200SPMV_ERR_STATE; }
+        if (short_rows && !use_rbs) return cs.run_f32(x, y, 0, nRow, CS_OVERWRITE, prec == 2, s);
+        return ts.run_rows_f32(x, y, CS_OVERWRITE, 0, nRow, prec == 2, s);
+    }
 
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
+        if (prec) { set_error("multiply: the handle was created with precision = %d, use b200spmv_multiply_f32", prec); return B200SPMV_ERR_STATE; }
         if (!short_rows) return ts.run_rows(x, y, CS_OVERWRITE, rb, re, s);
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
@@ -175,7 +183,7 @@ struct CrsFormat : Format {
     bool scalar(const std::string &n, long long *out) override
     {
         if (n == "alg_bytes") {   // 12 nnz + 4 (nRow+1) + 8 nCol + 8 nRow
-            *out = (f32 ? 8LL : 12LL) * nnz + 4LL * (nRow + 1) + 8LL * nCol + 8LL * nRow;
+            *out = (f32 ? 8LL : 12LL) * nnz + 4LL * (nRow + 1) + (prec ? 4LL : 8LL) * ((long long)nCol + nRow);
             return true;
         }
         if (n == "launches") { *out = short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
@@ -183,6 +191,7 @@ struct CrsFormat : Format {
         if (n == "short_row_path") { *out = short_rows ? 1 : 0; return true; }
         if (n == "nTiles") { *out = ts.nTiles; return true; }
         if (n == "value_f32") { *out = f32 ? 1 : 0; return true; }
+        if (n == "precision") { *out = prec; return true; }
         return false;
     }
 

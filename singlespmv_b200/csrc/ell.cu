@@ -23,11 +23,11 @@ __global__ void ell_slice_groups_kernel(const int *__restrict__ ptr, int nRow, i
     if (lane == 0) groups[s] = (len + V - 1) / V;
 }
 
-template <int V>
+template <int V, typename VT>
 __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
                                 const double *__restrict__ val, int nRow, int nSlices,
                                 const long long *__restrict__ slice_off, int K, int *__restrict__ ecol,
-                                double *__restrict__ eval)
+                                VT *__restrict__ eval)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -44,17 +44,17 @@ __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restri
             // padding: col = slot index (opt_ell.cpp:48) for the reference's K slots; the extra slots that round a
             // slice up to V (k >= K, never exported) point at column 0 so that no gather leaves x when K is close to nCol
             ecol[at] = real ? col[b + k] : ((r < nRow && k < K) ? k : 0);
-            eval[at] = real ? val[b + k] : 0.0;
+            eval[at] = real ? (VT)val[b + k] : (VT)0;      // fp32 storage: rounded to nearest once, here
         }
 }
 
-template <int V> struct EllGroup {
+template <int V, typename VT> struct EllGroup {
     int c[V];
-    double v[V];
+    VT v[V];
 };
 
 template <int V>
-__device__ __forceinline__ void ell_load(EllGroup<V> &g, const int *ecol, const double *eval, size_t at,
+__device__ __forceinline__ void ell_load(EllGroup<V, double> &g, const int *ecol, const double *eval, size_t at,
                                          uint64_t pol)
 {
     if (V == 4) {
@@ -69,13 +69,48 @@ __device__ __forceinline__ void ell_load(EllGroup<V> &g, const int *ecol, const 
         g.v[0] = a.x; g.v[1] = a.y;
     }
 }
+template <int V>
+__device__ __forceinline__ void ell_load(EllGroup<V, float> &g, const int *ecol, const float *eval, size_t at,
+                                         uint64_t pol)
+{
+    if (V == 4) {
+        int4 c = ld_stream_i4(ecol + at, pol);
+        float4 a;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(eval + at), "l"(pol));
+        g.c[0] = c.x; g.c[1] = c.y; g.c[V - 2] = c.z; g.c[V - 1] = c.w;
+        g.v[0] = a.x; g.v[1] = a.y; g.v[V - 2] = a.z; g.v[V - 1] = a.w;
+    } else {
+        int2 c = ld_stream_i2(ecol + at, pol);
+        float2 a;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                     : "=f"(a.x), "=f"(a.y) : "l"(eval + at), "l"(pol));
+        g.c[0] = c.x; g.c[1] = c.y;
+        g.v[0] = a.x; g.v[1] = a.y;
+    }
+}
+
 
 // One lane per row; the K-loop runs in ascending slot order with unfused mul/add, i.e. the
-// reference's own order -> y is bit-identical to opt_ell.cpp / opt_crs.cpp.
-template <int V, int XM>
+// reference's own order -> y is bit-identical to opt_ell.cpp / opt_crs.cpp (fp64).
+// VT = stored value type, XT = type of x and y, AT = type of the products and the row sum.
+__device__ __forceinline__ double ell_gather(const double *p, uint64_t pol, int xm)
+{
+    switch (xm) {
+    case 1: return ld_x_mode<1>(p, pol);
+    case 2: return ld_x_mode<2>(p, pol);
+    case 3: return ld_x_mode<3>(p, pol);
+    case 4: return ld_x_mode<4>(p, pol);
+    case 5: return ld_x_mode<5>(p, pol);
+    default: return ld_x_mode<0>(p, pol);
+    }
+}
+__device__ __forceinline__ float ell_gather(const float *p, uint64_t pol, int) { return ld_x(p, pol); }
+
+template <int V, int XM, typename VT, typename XT, typename AT>
 __global__ void __launch_bounds__(256)
 ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
-                const double *__restrict__ eval, const double *__restrict__ x, double *__restrict__ y,
+                const VT *__restrict__ eval, const XT *__restrict__ x, XT *__restrict__ y,
                 int rowBegin, int rowEnd, int sliceBegin, int sliceEnd)
 {
     const int s = sliceBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -83,39 +118,39 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
     if (s >= sliceEnd) return;
     const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
     const long long g0 = slice_off[s], g1 = slice_off[s + 1];
-    double acc = 0.0;
+    AT acc = (AT)0;
     long long g = g0;
     for (; g + 2 <= g1; g += 2) {
-        EllGroup<V> a, b;
+        EllGroup<V, VT> a, b;
         ell_load<V>(a, ecol, eval, ((size_t)g * 32 + lane) * V, pol_stream);
         ell_load<V>(b, ecol, eval, ((size_t)(g + 1) * 32 + lane) * V, pol_stream);
-        double xa[V], xb[V];
+        XT xa[V], xb[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) xa[j] = ld_x_mode<XM>(x + a.c[j], pol_x);
+        for (int j = 0; j < V; j++) xa[j] = ell_gather(x + a.c[j], pol_x, XM);
 #pragma unroll
-        for (int j = 0; j < V; j++) xb[j] = ld_x_mode<XM>(x + b.c[j], pol_x);
+        for (int j = 0; j < V; j++) xb[j] = ell_gather(x + b.c[j], pol_x, XM);
 #pragma unroll
-        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
+        for (int j = 0; j < V; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)xa[j], (AT)a.v[j]));
 #pragma unroll
-        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xb[j], b.v[j]));
+        for (int j = 0; j < V; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)xb[j], (AT)b.v[j]));
     }
     if (g < g1) {
-        EllGroup<V> a;
+        EllGroup<V, VT> a;
         ell_load<V>(a, ecol, eval, ((size_t)g * 32 + lane) * V, pol_stream);
-        double xa[V];
+        XT xa[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) xa[j] = ld_x_mode<XM>(x + a.c[j], pol_x);
+        for (int j = 0; j < V; j++) xa[j] = ell_gather(x + a.c[j], pol_x, XM);
 #pragma unroll
-        for (int j = 0; j < V; j++) acc = __dadd_rn(acc, __dmul_rn(xa[j], a.v[j]));
+        for (int j = 0; j < V; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)xa[j], (AT)a.v[j]));
     }
     const int r = s * 32 + lane;
-    if (r >= rowBegin && r < rowEnd) y[r] = acc;
+    if (r >= rowBegin && r < rowEnd) y[r] = (XT)acc;
 }
 
 // Logical [nRow][K] view for parity checks (slots beyond the slice width are padding).
-template <int V>
+template <int V, typename VT>
 __global__ void ell_logical_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
-                                   const double *__restrict__ eval, int nRow, int K, int *__restrict__ lcol,
+                                   const VT *__restrict__ eval, int nRow, int K, int *__restrict__ lcol,
                                    double *__restrict__ lval)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,7 +161,7 @@ __global__ void ell_logical_kernel(const long long *__restrict__ slice_off, cons
     if (k < (int)(g1 - g0) * V) {
         const size_t at = ((size_t)(g0 + k / V) * 32 + lane) * V + k % V;
         lcol[i] = ecol[at];
-        lval[i] = eval[at];
+        lval[i] = (double)eval[at];
     } else {
         lcol[i] = k;
         lval[i] = 0.0;
@@ -139,9 +174,11 @@ struct EllFormat : Format {
     DevBuf<long long> slice_off;
     DevBuf<int> ecol;
     DevBuf<double> eval;
+    DevBuf<float> eval32;             // options.precision = 1 / 2: fp32 value storage
+    int prec = 0;
     std::unique_ptr<ColBlockEngine> cb;   // column-blocked multiply layout when x does not fit L2 (colblocks.cuh)
     int cbs_want = 0;
-    explicit EllFormat(const b200spmv_options &o) : cbs_want(o.col_blocks) {}
+    explicit EllFormat(const b200spmv_options &o) : prec(o.precision), cbs_want(o.col_blocks) {}
 
     template <int VV> int convert_t(const CooView &A, const int *ptr, cudaStream_t s)
     {
@@ -155,10 +192,12 @@ struct EllFormat : Format {
         B2_CUDA(cudaMemcpy(&totalGroups, slice_off.p + nSlices, sizeof(long long), cudaMemcpyDeviceToHost));
         slots = totalGroups * 32 * VV;
         B2_TRY(ecol.alloc((size_t)slots));
-        B2_TRY(eval.alloc((size_t)slots));
+        if (prec) B2_TRY(eval32.alloc((size_t)slots));
+        else B2_TRY(eval.alloc((size_t)slots));
         if (nSlices) {
-            ell_fill_kernel<VV><<<ceil_div((long long)nSlices * 32, 256), 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices,
-                                                                                      slice_off.p, K, ecol.p, eval.p);
+            const int grid = ceil_div((long long)nSlices * 32, 256);
+            if (prec) ell_fill_kernel<VV, float><<<grid, 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices, slice_off.p, K, ecol.p, eval32.p);
+            else ell_fill_kernel<VV, double><<<grid, 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices, slice_off.p, K, ecol.p, eval.p);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -180,13 +219,26 @@ struct EllFormat : Format {
         nSlices = ceil_div(nRow, 32);
         int st = V == 4 ? convert_t<4>(A, ptr.p, s) : convert_t<2>(A, ptr.p, s);
         B2_TRY(st);
-        B2_TRY(make_col_block_engine(A, ptr.p, cbs_want, s, &cb));
+        cb.reset();
+        if (!prec) B2_TRY(make_col_block_engine(A, ptr.p, cbs_want, s, &cb));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
-    bool has_rows() const override { return !(cb != nullptr); }   // a row chunk would pay every column-block switch again
+    int multiply_f32(const float *x, float *y, cudaStream_t s) override
+    {
+        if (!prec) { set_error("multiply_f32: the handle was created with precision = 0 (fp64 vectors)"); return B200SPMV_ERR_STATE; }
+        if (nRow == 0) return B200SPMV_OK;
+        const int blocks = ceil_div((long long)nSlices * 32, 256);
+        if (V == 4 && prec == 1) ell_spmv_kernel<4, 0, float, float, float><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval32.p, x, y, 0, nRow, 0, nSlices);
+        else if (V == 4) ell_spmv_kernel<4, 0, float, float, double><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval32.p, x, y, 0, nRow, 0, nSlices);
+        else if (prec == 1) ell_spmv_kernel<2, 0, float, float, float><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval32.p, x, y, 0, nRow, 0, nSlices);
+        else ell_spmv_kernel<2, 0, float, float, double><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval32.p, x, y, 0, nRow, 0, nSlices);
+        B2_KERNEL_CHECK();
+        return B200SPMV_OK;
+    }
+    bool has_rows() const override { return !(cb != nullptr) && !prec; }   // a row chunk would pay every column-block switch again
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
@@ -202,11 +254,12 @@ struct EllFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (prec) { set_error("multiply: the handle was created with precision = %d, use b200spmv_multiply_f32", prec); return B200SPMV_ERR_STATE; }
         if (rb == re) return B200SPMV_OK;
         if ((cb != nullptr)) return cb->run(x, y, rb, re, s);
         const int sb = rb / 32, se = ceil_div(re, 32);
         const int blocks = ceil_div((long long)(se - sb) * 32, 256);
-#define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, rb, re, sb, se)
+#define ELL_LAUNCH(VV, XM) ell_spmv_kernel<VV, XM, double, double, double><<<blocks, 256, 0, s>>>(slice_off.p, ecol.p, eval.p, x, y, rb, re, sb, se)
 #define ELL_LAUNCH_V(VV)                                   \
     switch (xload_mode()) {                                \
     case 1: ELL_LAUNCH(VV, 1); break;                      \
@@ -227,11 +280,12 @@ struct EllFormat : Format {
         if (n == "slots") { *out = slots; return true; }
         if (n == "slice_vec") { *out = V; return true; }
         if (n == "alg_bytes") {   // 12 B per stored slot + slice offsets + x + y
-            *out = 12LL * slots + 8LL * (nSlices + 1) + 8LL * nCol + 8LL * nRow;
+            *out = (prec ? 8LL : 12LL) * slots + 8LL * (nSlices + 1) + (prec ? 4LL : 8LL) * ((long long)nCol + nRow);
             return true;
         }
         if (n == "launches") { *out = (cb != nullptr) ? cb->n_blocks() : 1; return true; }
         if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
+        if (n == "precision") { *out = prec; return true; }
         return false;
     }
 
@@ -245,8 +299,11 @@ struct EllFormat : Format {
         DevBuf<double> lval;
         if (lcol.alloc(cnt) || lval.alloc(cnt)) return B200SPMV_ERR_NOMEM;
         if (cnt) {
-            if (V == 4) ell_logical_kernel<4><<<ceil_div((long long)cnt, 256), 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
-            else ell_logical_kernel<2><<<ceil_div((long long)cnt, 256), 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
+            const int grid = ceil_div((long long)cnt, 256);
+            if (V == 4 && prec) ell_logical_kernel<4, float><<<grid, 256>>>(slice_off.p, ecol.p, eval32.p, nRow, K, lcol.p, lval.p);
+            else if (V == 4) ell_logical_kernel<4, double><<<grid, 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
+            else if (prec) ell_logical_kernel<2, float><<<grid, 256>>>(slice_off.p, ecol.p, eval32.p, nRow, K, lcol.p, lval.p);
+            else ell_logical_kernel<2, double><<<grid, 256>>>(slice_off.p, ecol.p, eval.p, nRow, K, lcol.p, lval.p);
         }
         return export_device(isCol ? (const void *)lcol.p : (const void *)lval.p, bytes, dst, cap);
     }

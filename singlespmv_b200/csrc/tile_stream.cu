@@ -48,21 +48,34 @@ __device__ __forceinline__ double ld_val1(const float *p, uint64_t pol)
     return (double)r;
 }
 
+// four consecutive products to shared memory with 128-bit stores (p is 16-byte aligned for float, 32 for double)
+__device__ __forceinline__ void st_prod4(double *p, double a, double b, double c, double d)
+{
+    reinterpret_cast<double2 *>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
+}
+__device__ __forceinline__ void st_prod4(float *p, float a, float b, float c, float d)
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+
 // TMA = true: the tile's col / val slices are brought into shared memory by two 1-D bulk copies issued by one thread
 // (cp.async.bulk, SASS UBLKCP) instead of through every thread's load pipeline.  An SM sustains about one L1-missing
 // sector per clock (profiles/r2_gather_ceiling.md); on gather-bound matrices the x gathers need all of that, so the
-// 12 B/nnz matrix stream is taken off it.  The products overwrite the staged values in place.
-template <typename VT, int TH, bool TMA>
+// 12 B/nnz matrix stream is taken off it.  The products overwrite the staged values in place when the types allow.
+// VT = stored value type, XT = type of x and y, AT = type of the products and sums.
+template <typename VT, typename XT, typename AT, int TH, bool TMA>
 __global__ void __launch_bounds__(TH)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const int *__restrict__ tile_row,
-                   const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry,
-                   int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok)
+                   const XT *__restrict__ x, XT *__restrict__ y, double *__restrict__ carry,
+                   int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok, int tma_policy)
 {
     constexpr int TILE = TH * TS_IPT;
-    __shared__ __align__(16) double prod[TILE];
+    constexpr bool INPLACE = sizeof(VT) == sizeof(AT);
+    __shared__ __align__(16) AT prod[TILE];
     __shared__ __align__(16) int scol[TMA ? TILE : 4];
-    __shared__ __align__(16) VT sval32[(TMA && sizeof(VT) == 4) ? TILE : 4];   // fp32 values cannot share prod's slots
+    __shared__ __align__(16) VT sval_own[(TMA && !INPLACE) ? TILE : 4];      // values that cannot share prod's slots
     __shared__ __align__(8) uint64_t bar;
     __shared__ int long_row[TILE / TS_LONG + 2];
     __shared__ int n_long;
@@ -77,19 +90,29 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
 
     // ---- phase 1: stream the tile, gather x, park products in shared memory
     if (TMA) {
-        VT *sval = sizeof(VT) == 8 ? reinterpret_cast<VT *>(prod) : sval32;
+        VT *sval = INPLACE ? reinterpret_cast<VT *>(prod) : sval_own;
         const int n = t1 - t0;
         if (tid == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (tid == 0) {
             const uint32_t bytesI = (uint32_t)((n * 4 + 15) & ~15), bytesV = (uint32_t)((n * (int)sizeof(VT) + 15) & ~15);
             mbar_expect_tx(&bar, bytesI + bytesV);
-            tma_load_1d(scol, col + t0, bytesI, &bar, pol_stream);
-            tma_load_1d(sval, val + t0, bytesV, &bar, pol_stream);
+            if (tma_policy == 2) {                      // experiment: no L2 hint at all
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(scol)), "l"(col + t0), "r"(bytesI), "r"(smem_u32(&bar)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sval)), "l"(val + t0), "r"(bytesV), "r"(smem_u32(&bar)) : "memory");
+            } else {
+                uint64_t pol = pol_stream;
+                if (tma_policy == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+                if (tma_policy == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+                tma_load_1d(scol, col + t0, bytesI, &bar, pol);
+                tma_load_1d(sval, val + t0, bytesV, &bar, pol);
+            }
         }
         mbar_wait(&bar, 0);
         if (n == TILE) {
-            double xs[TS_IPT];
+            XT xs[TS_IPT];
             int4 c[TS_IPT / 4];
 #pragma unroll
             for (int k = 0; k < TS_IPT / 4; k++) c[k] = *reinterpret_cast<const int4 *>(scol + 4 * (tid + k * TH));
@@ -103,15 +126,21 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
 #pragma unroll
             for (int k = 0; k < TS_IPT / 4; k++) {
                 const int o = 4 * (tid + k * TH);
-                const double v0 = (double)sval[o], v1 = (double)sval[o + 1], v2 = (double)sval[o + 2], v3 = (double)sval[o + 3];
-                double2 *dst = reinterpret_cast<double2 *>(prod + o);
-                dst[0] = make_double2(__dmul_rn(v0, xs[4 * k]), __dmul_rn(v1, xs[4 * k + 1]));
-                dst[1] = make_double2(__dmul_rn(v2, xs[4 * k + 2]), __dmul_rn(v3, xs[4 * k + 3]));
+                VT vv[4];
+                if (sizeof(VT) == 8) {
+                    *reinterpret_cast<double2 *>(vv) = *reinterpret_cast<const double2 *>(sval + o);
+                    *reinterpret_cast<double2 *>(vv + 2) = *reinterpret_cast<const double2 *>(sval + o + 2);
+                } else {
+                    *reinterpret_cast<float4 *>(vv) = *reinterpret_cast<const float4 *>(sval + o);
+                }
+                const AT v0 = (AT)vv[0], v1 = (AT)vv[1], v2 = (AT)vv[2], v3 = (AT)vv[3];
+                st_prod4(prod + o, Arith<AT>::mul(v0, (AT)xs[4 * k]), Arith<AT>::mul(v1, (AT)xs[4 * k + 1]),
+                         Arith<AT>::mul(v2, (AT)xs[4 * k + 2]), Arith<AT>::mul(v3, (AT)xs[4 * k + 3]));
             }
         } else {
             for (int i = tid; i < n; i += TH) {
-                const double v = (double)sval[i];
-                prod[i] = __dmul_rn(v, ld_x(x + scol[i], pol_x));
+                const AT v = (AT)sval[i];
+                prod[i] = Arith<AT>::mul(v, (AT)ld_x(x + scol[i], pol_x));
             }
         }
     } else if (t1 - t0 == TILE && vec_ok) {
@@ -123,7 +152,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
             c[k] = ld_stream_i4(col + e, pol_stream);
             ld_val4(val + e, pol_stream, v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
         }
-        double xs[TS_IPT];
+        XT xs[TS_IPT];
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
             xs[4 * k + 0] = ld_x(x + c[k].x, pol_x);
@@ -133,15 +162,14 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
         }
 #pragma unroll
         for (int k = 0; k < TS_IPT / 4; k++) {
-            double2 *dst = reinterpret_cast<double2 *>(prod + 4 * (tid + k * TH));
-            dst[0] = make_double2(__dmul_rn(v[2 * k].x, xs[4 * k]), __dmul_rn(v[2 * k].y, xs[4 * k + 1]));
-            dst[1] = make_double2(__dmul_rn(v[2 * k + 1].x, xs[4 * k + 2]),
-                                  __dmul_rn(v[2 * k + 1].y, xs[4 * k + 3]));
+            const int o = 4 * (tid + k * TH);
+            st_prod4(prod + o, Arith<AT>::mul((AT)v[2 * k].x, (AT)xs[4 * k]), Arith<AT>::mul((AT)v[2 * k].y, (AT)xs[4 * k + 1]),
+                     Arith<AT>::mul((AT)v[2 * k + 1].x, (AT)xs[4 * k + 2]), Arith<AT>::mul((AT)v[2 * k + 1].y, (AT)xs[4 * k + 3]));
         }
     } else {
         for (int i = tid; i < t1 - t0; i += TH)
-            prod[i] = __dmul_rn(ld_val1(val + t0 + i, pol_stream),
-                                ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
+            prod[i] = Arith<AT>::mul((AT)ld_val1(val + t0 + i, pol_stream),
+                                     (AT)ld_x(x + ld_stream_i1(col + t0 + i, pol_stream), pol_x));
     }
 
     const int r_lo = tile_row[t], r_hi = tile_row[t + 1];
@@ -159,9 +187,9 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
             long_row[atomicAdd(&n_long, 1)] = r;
             continue;
         }
-        double acc = accumulate == CS_CONTINUE ? y[r] : 0.0;          // CONTINUE: the running sum of the earlier column blocks
-        for (int j = b; j < e; j++) acc = __dadd_rn(acc, prod[j - t0]);
-        y[r] = accumulate == CS_ADD ? __dadd_rn(y[r], acc) : acc;
+        AT acc = accumulate == CS_CONTINUE ? (AT)y[r] : (AT)0;    // CONTINUE: the running sum of the earlier column blocks
+        for (int j = b; j < e; j++) acc = Arith<AT>::add(acc, prod[j - t0]);
+        y[r] = (XT)(accumulate == CS_ADD ? Arith<AT>::add((AT)y[r], acc) : acc);
     }
     if (tid == 0 && cin_end > t0) {
         const int rc = r_lo - 1;
@@ -170,7 +198,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     }
     __syncthreads();
 
-    // ---- phase 2b: one warp per long row / carried-in piece
+    // ---- phase 2b: one warp per long row / carried-in piece (fp64 tree whatever AT is: a handful of adds per row)
     const int lane = tid & 31, warp = tid >> 5;
     const int nl = n_long;
     for (int i = warp; i < nl; i += TH / 32) {
@@ -184,21 +212,21 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
             e = min(row_ptr[r + 1], t1);
         }
         double acc = 0.0;
-        for (int j = b + lane; j < e; j += 32) acc += prod[j - t0];
+        for (int j = b + lane; j < e; j += 32) acc += (double)prod[j - t0];
         acc = warp_sum(acc);
         if (lane == 0) {
             if (r < 0) carry[t] = acc;
-            else y[r] = accumulate ? y[r] + acc : acc;
+            else y[r] = (XT)(accumulate ? (double)y[r] + acc : acc);
         }
     }
 }
 
 // Finishes the rows that cross tile boundaries; one thread per tile, only the FIRST carrying
 // tile of a row acts.  Short rows are recomputed from global memory in the reference's order.
-template <typename VT>
+template <typename VT, typename XT, typename AT>
 __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                                   const VT *__restrict__ val, const int *__restrict__ tile_row,
-                                  const double *__restrict__ x, double *__restrict__ y,
+                                  const XT *__restrict__ x, XT *__restrict__ y,
                                   const double *__restrict__ carry, int tileLo, int tileHi, int rowLo,
                                   int rowHi, int accumulate, int tile)
 {
@@ -213,14 +241,14 @@ __global__ void tile_fixup_kernel(const int *__restrict__ row_ptr, const int *__
     const int b = row_ptr[rc];
     if (t != b / tile + 1) return;
     if (e - b <= TS_LONG) {
-        double acc = accumulate == CS_CONTINUE ? y[rc] : 0.0;
-        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn((double)val[j], x[col[j]]));
-        y[rc] = accumulate == CS_ADD ? __dadd_rn(y[rc], acc) : acc;
+        AT acc = accumulate == CS_CONTINUE ? (AT)y[rc] : (AT)0;
+        for (int j = b; j < e; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)val[j], (AT)x[col[j]]));
+        y[rc] = (XT)(accumulate == CS_ADD ? Arith<AT>::add((AT)y[rc], acc) : acc);
     } else {
         const int last = (e - 1) / tile;
         double sum = 0.0;
         for (int u = t; u <= last; u++) sum += carry[u];
-        y[rc] += sum;
+        y[rc] = (XT)((double)y[rc] + sum);
     }
 }
 
@@ -290,6 +318,41 @@ int TileStream::prepare(int rb, int re)
     return B200SPMV_OK;
 }
 
+template <typename VT, typename XT, typename AT>
+static int ts_launch(const TileStream &T, const XT *x, XT *y, int acc, int rowLo, int rowHi, int tileLo, int tileHi, cudaStream_t s)
+{
+    const VT *v = static_cast<const VT *>(T.val);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(T.col) | reinterpret_cast<uintptr_t>(T.val)) & 15) == 0;
+    const int nT = tileHi - tileLo;
+    const bool fix = nT > 1 || tileLo > 0;
+    // bulk copies need 16-byte aligned slices and may read up to 15 bytes past the last entry (callers keep CS_SLACK)
+    const bool use_tma = T.tma && vec_ok && T.threads <= 256;
+    static bool carveout_set = false;
+    if (use_tma && !carveout_set) {       // 8 resident CTAs x 24.7 KB: ask for the large shared-memory split once
+        carveout_set = true;
+        cudaFuncSetAttribute(tile_stream_kernel<VT, XT, AT, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(tile_stream_kernel<VT, XT, AT, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
+    }
+    static const int tma_policy = getenv("B200SPMV_TMA_POLICY") ? atoi(getenv("B200SPMV_TMA_POLICY")) : 0;
+#define TS_ARGS T.row_ptr, T.col, v, T.tile_row.p, x, y, T.carry.p, T.nnz, tileLo, rowLo, rowHi, acc, vec_ok, tma_policy
+    if (T.threads == 128) {
+        if (use_tma) tile_stream_kernel<VT, XT, AT, 128, true><<<nT, 128, 0, s>>>(TS_ARGS);
+        else tile_stream_kernel<VT, XT, AT, 128, false><<<nT, 128, 0, s>>>(TS_ARGS);
+    } else if (T.threads == 512) {
+        tile_stream_kernel<VT, XT, AT, 512, false><<<nT, 512, 0, s>>>(TS_ARGS);
+    } else {
+        if (use_tma) tile_stream_kernel<VT, XT, AT, 256, true><<<nT, 256, 0, s>>>(TS_ARGS);
+        else tile_stream_kernel<VT, XT, AT, 256, false><<<nT, 256, 0, s>>>(TS_ARGS);
+    }
+#undef TS_ARGS
+    if (fix)
+        tile_fixup_kernel<VT, XT, AT><<<ceil_div(nT, 256), 256, 0, s>>>(T.row_ptr, T.col, v, T.tile_row.p, x, y, T.carry.p, tileLo,
+                                                                        tileHi, rowLo, rowHi, acc, T.tile);
+    B2_KERNEL_CHECK();
+    return B200SPMV_OK;
+}
+
 int TileStream::run(const double *x, double *y, int accumulate, int rowLo, int rowHi, int tileLo,
                     int tileHi, cudaStream_t s) const
 {
@@ -298,39 +361,29 @@ int TileStream::run(const double *x, double *y, int accumulate, int rowLo, int r
         if (!accumulate) B2_CUDA(cudaMemsetAsync(y + rowLo, 0, sizeof(double) * (size_t)(rowHi - rowLo), s));
         return B200SPMV_OK;
     }
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(val)) & 15) == 0;
-    const int nT = tileHi - tileLo, acc = accumulate;
-    const bool fix = nT > 1 || tileLo > 0;
-    // bulk copies need 16-byte aligned slices and may read up to 15 bytes past the last entry (callers keep CS_SLACK)
-    const bool use_tma = tma && vec_ok;
-    static bool carveout_set = false;
-    if (use_tma && !carveout_set) {       // 8 resident CTAs x 24.7 KB: ask for the large shared-memory split once
-        carveout_set = true;
-        cudaFuncSetAttribute(tile_stream_kernel<double, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(tile_stream_kernel<float, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(tile_stream_kernel<double, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(tile_stream_kernel<float, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaGetLastError();
+    if (f32) return ts_launch<float, double, double>(*this, x, y, accumulate, rowLo, rowHi, tileLo, tileHi, s);
+    return ts_launch<double, double, double>(*this, x, y, accumulate, rowLo, rowHi, tileLo, tileHi, s);
+}
+
+// fp32 vectors over fp32 values; acc64: products and sums in fp64
+int TileStream::run_rows_f32(const float *x, float *y, int accumulate, int rb, int re, bool acc64, cudaStream_t s)
+{
+    if (!f32) { set_error("tile-stream: fp32 vectors need fp32 value storage"); return B200SPMV_ERR_STATE; }
+    if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d) for %d rows", rb, re, nRow); return B200SPMV_ERR_INVALID; }
+    if (rb == re) return B200SPMV_OK;
+    int lo = 0, hi = nTiles;
+    if (!(rb == 0 && re == nRow)) {
+        B2_TRY(prepare(rb, re));
+        const auto it = range_cache.find(std::make_pair(rb, re));
+        lo = it->second.first;
+        hi = it->second.second;
     }
-#define TS_LAUNCH(VT, TH, v)                                                                                                      \
-    do {                                                                                                                          \
-        if (use_tma && TH <= 256) tile_stream_kernel<VT, (TH <= 256 ? TH : 256), true><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
-        else tile_stream_kernel<VT, TH, false><<<nT, TH, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, nnz, tileLo, rowLo, rowHi, acc, vec_ok); \
-        if (fix) tile_fixup_kernel<VT><<<ceil_div(nT, 256), 256, 0, s>>>(row_ptr, col, v, tile_row.p, x, y, carry.p, tileLo, tileHi, rowLo, rowHi, acc, tile); \
-    } while (0)
-    if (f32) {
-        const float *v = static_cast<const float *>(val);
-        if (threads == 128) TS_LAUNCH(float, 128, v);
-        else if (threads == 512) TS_LAUNCH(float, 512, v);
-        else TS_LAUNCH(float, 256, v);
-    } else {
-        const double *v = static_cast<const double *>(val);
-        if (threads == 128) TS_LAUNCH(double, 128, v);
-        else if (threads == 512) TS_LAUNCH(double, 512, v);
-        else TS_LAUNCH(double, 256, v);
+    if (nTiles == 0) {
+        if (!accumulate) B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(float) * (size_t)(re - rb), s));
+        return B200SPMV_OK;
     }
-    B2_KERNEL_CHECK();
-    return B200SPMV_OK;
+    if (acc64) return ts_launch<float, float, double>(*this, x, y, accumulate, rb, re, lo, hi, s);
+    return ts_launch<float, float, float>(*this, x, y, accumulate, rb, re, lo, hi, s);
 }
 
 }  // namespace b2

@@ -61,6 +61,7 @@ struct TileStream {
     // rows [rb, re) only: looks up (and caches) the tiles that hold their entries
     int run_rows(const double *x, double *y, int accumulate, int rb, int re, cudaStream_t s);
     int prepare(int rb, int re);
+    int run_rows_f32(const float *x, float *y, int accumulate, int rb, int re, bool acc64, cudaStream_t s);
     size_t meta_bytes() const { return tile_row.bytes(); }
     std::map<std::pair<int, int>, std::pair<int, int>> range_cache;
 };

@@ -99,12 +99,12 @@ class SpMatOpt:
     ``scalar(name)`` / ``array(name, dtype)`` read the fields back under the reference's names, in the
     reference's logical layout, for parity checks."""
 
-    def __init__(self, fmt, segment_width=0, n_block=0, csr5_sigma=0, ss_faithful=0, value_f32=0, crs_path=0, profile=0, col_blocks=0, hyb_k=0):
+    def __init__(self, fmt, segment_width=0, n_block=0, csr5_sigma=0, ss_faithful=0, value_f32=0, crs_path=0, profile=0, col_blocks=0, hyb_k=0, precision=0):
         self.fmt = fmt
         o = Options()
         o.segment_width, o.n_block, o.csr5_sigma, o.ss_faithful = segment_width, n_block, csr5_sigma, ss_faithful
         o.value_f32, o.crs_path, o.profile, o.col_blocks = value_f32, crs_path, profile, col_blocks
-        o.hyb_k = hyb_k
+        o.hyb_k, o.precision = hyb_k, precision
         self.h = C.c_void_p()
         check(lib.b200spmv_create(FORMATS[fmt], C.byref(o), C.byref(self.h)))
         self.nRow = self.nCol = self.nNnz = 0
@@ -160,6 +160,14 @@ class SpMatOpt:
         lo, hi = C.c_int(), C.c_int()
         check(lib.b200spmv_rows_col_extent(self.h, row_begin, row_end, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def multiply_f32(self, x_ptr, y_ptr, stream=None):
+        """fp32 vectors (handle created with precision=1 or 2); raw device addresses of float arrays."""
+        check(lib.b200spmv_multiply_f32(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), stream))
+
+    def multiply_host_f32(self, x, y):
+        assert x.dtype == np.float32 and y.dtype == np.float32
+        check(lib.b200spmv_multiply_host_f32(self.h, _ptr(x), _ptr(y)))
 
     def multiply_host(self, x, y):
         check(lib.b200spmv_multiply_host(self.h, _ptr(x), _ptr(y)))

@@ -911,3 +911,74 @@ def test_css_blocks_on_row_chunk_stream(sp, oracle, kind, n, maxlen):
         assert_y(y, y_ref, row, col, val, x, nr)
         if nb == 1:
             assert np.array_equal(y, y_ref)
+
+
+# ------------------------------------------------------------------------------------------ fp32 variant
+@pytest.mark.parametrize("fmt", ["crs", "ell"])
+@pytest.mark.parametrize("precision", [1, 2])
+def test_fp32_variant(sp, oracle, all_cases, fmt, precision):
+    """options.precision: fp32 matrix values, fp32 x and y; sums in fp32 (1) or fp64 (2).  BASELINE.json's bar: within 1e-5
+    of the reference's (fp64) CRS result per row, relative to |y_ref| or to sum_j |a_ij x_j|.  With fp64 sums only the
+    rounding of the inputs remains (<= 1.2e-7); with fp32 sums a row of n entries may drift by n * 2^-24, so rows of
+    more than 64 entries get the bound their length implies."""
+    import torch
+    for name, nRow, nCol, row, col, val, x in all_cases:
+        lens = np.bincount(row, minlength=nRow) if len(row) else np.zeros(nRow, np.int64)
+        K = int(lens.max()) if nRow else 0
+        if fmt == "ell" and (K > nCol or K * nRow > 5e7):
+            continue
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        mag = np.zeros(nRow)
+        np.add.at(mag, row, np.abs(val * x[col]))
+        A_opt = sp.SpMatOpt(fmt, precision=precision).convert_host(sp.SpMat(nRow, nCol, row, col, val))
+        assert A_opt.scalar("precision") == precision
+        if fmt == "crs":
+            assert A_opt.scalar("alg_bytes") == 8 * len(row) + 4 * (nRow + 1) + 4 * nCol + 4 * nRow
+            assert np.array_equal(A_opt.array("val", np.float64), val.astype(np.float32).astype(np.float64))
+        x32 = x.astype(np.float32)
+        y32 = np.full(nRow, np.nan, np.float32)
+        A_opt.multiply_host_f32(x32, y32)
+        xd = torch.from_numpy(x32).cuda()
+        yd = torch.full((max(nRow, 1),), float("nan"), dtype=torch.float32, device="cuda")
+        A_opt.multiply_f32(xd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(yd.cpu().numpy()[:nRow], y32), name        # host-semantics = device-resident
+        assert np.all(np.isfinite(y32)), name
+        err = np.abs(y32.astype(np.float64) - y_ref)
+        tol = np.full(nRow, 1e-5)
+        if precision == 1:
+            tol = np.maximum(tol, lens * 2.0 ** -23)
+        ok = (err <= tol * np.abs(y_ref)) | (err <= tol * mag)
+        assert np.all(ok), (name, int((~ok).sum()), float(np.max(err / np.maximum(mag, 1e-300))))
+        with pytest.raises(sp.B200SpmvError) as e:                        # fp64 entry on an fp32 handle
+            A_opt.multiply_host(x, np.empty(nRow))
+        assert e.value.status == -4 or nRow == 0
+    plain = sp.SpMatOpt(fmt).convert_host(sp.SpMat(3, 3, np.array([0], np.int32), np.array([1], np.int32), np.array([1.0])))
+    with pytest.raises(sp.B200SpmvError) as e:
+        plain.multiply_host_f32(np.ones(3, np.float32), np.ones(3, np.float32))
+    assert e.value.status == -4
+    with pytest.raises(sp.B200SpmvError) as e:
+        sp.SpMatOpt("jds", precision=1)
+    assert e.value.status == -3
+
+
+def test_fp32_full_size_c5(sp):
+    """Config 5 at full size in fp32: A.1 row sums are small integers (exact in fp32), so the result must be exact."""
+    import torch
+    d = sp.DeviceCoo("lap3d7", 256)
+    n = d.nRow
+    for fmt in ("crs", "ell"):
+        A = sp.SpMatOpt(fmt, precision=1).convert_device(d)
+        x = torch.ones(n, dtype=torch.float32, device="cuda")
+        y = torch.full((n,), float("nan"), dtype=torch.float32, device="cuda")
+        A.multiply_f32(x.data_ptr(), y.data_ptr())
+        torch.cuda.synchronize()
+        B = sp.SpMatOpt(fmt).convert_device(d)
+        x64 = torch.ones(n, dtype=torch.float64, device="cuda")
+        y64 = torch.empty(n, dtype=torch.float64, device="cuda")
+        B.multiply(x64.data_ptr(), y64.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(y.double(), y64), fmt
+        A.destroy()
+        B.destroy()
+    d.free()

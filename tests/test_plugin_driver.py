@@ -102,7 +102,8 @@ def test_driver_report_keys_of_the_reference(built):
     """Keys the reference's report carries and log/format consumers read (src/main.cpp:155-174,200-206): nThread for
     every format; nStep + StepCount-xx for SS; MulPerf / SumPerf for the -DPROFILING builds of SS and CSS."""
     env = dict(os.environ, SPMV_MIN_SECONDS="0.02", SPMV_NTRY="2")
-    r = subprocess.run([os.path.join(built, "spmv_b200_ss_dev"), "synth:lap2d5:64"], capture_output=True, text=True, timeout=120, env=env)
+    # 27 entries per row, W = 4: rows span chains of whole segments -> at least two fold steps (src/opt_ss.cpp:91-142)
+    r = subprocess.run([os.path.join(built, "spmv_b200_ss_dev"), "synth:box3d27:12"], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     kv = parse_report(r.stdout)
     assert kv["nThread"] == "1" and kv["nGPU"] == "1"
@@ -110,7 +111,7 @@ def test_driver_report_keys_of_the_reference(built):
     assert n >= 1 and all(("StepCount-%02d" % i) in kv for i in range(n))
     assert sum(int(kv["StepCount-%02d" % i]) for i in range(n)) > 0
     for exe, keys in (("spmv_b200_ss_prof", ("MulPerf", "SumPerf")), ("spmv_b200_css_prof", ("MulPerf(GFLOPS)", "SumPerf(GFLOPS)"))):
-        r = subprocess.run([os.path.join(built, exe), "synth:lap2d5:64"], capture_output=True, text=True, timeout=120, env=env)
+        r = subprocess.run([os.path.join(built, exe), "synth:box3d27:12"], capture_output=True, text=True, timeout=120, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         kv = parse_report(r.stdout)
         assert all(float(kv[k]) > 0 for k in keys), kv
