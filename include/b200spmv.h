@@ -197,6 +197,29 @@ B200SPMV_API int b200spmv_partition_rows(const int *row_d /* sorted COO row ids 
 /* the same split for a synthetic matrix, from its row lengths alone (nothing is generated) */
 B200SPMV_API int b200spmv_partition_synth(int kind, long long p0, long long p1, int nParts, int *bounds_h);
 
+/* ---- the same multiply with ONE process driving all GPUs (csrc/mg.cu): what the C++ plugin uses with -DB200_NGPU=N so
+ * that the reference's driver loop (src/main.cpp:58-102) runs over 8 B200s like over one.  Partition and halo
+ * renumbering as above; the halo is PULLED by a kernel out of the owners' x slices through NVLink peer mappings, overlapped
+ * with the interior rows, and the whole step of all GPUs is one multi-device CUDA graph launch.  Square matrices. */
+typedef struct b200spmv_mg b200spmv_mg;
+B200SPMV_API int b200spmv_mg_create(int nGPU, int format, const b200spmv_options *opts /* may be NULL */, b200spmv_mg **out);
+B200SPMV_API int b200spmv_mg_destroy(b200spmv_mg *m);
+/* any sorted COO on the host (e.g. what src/util.cpp:30-66 loads): split by non-zero balance, one block per GPU */
+B200SPMV_API int b200spmv_mg_convert_coo_host(b200spmv_mg *m, int nRow, int nCol, long long nnz, const int *row_h,
+                                 const int *col_h, const double *val_h);
+/* synthetic matrix (b200spmv_synth kinds except RMAT): every GPU generates its own rows in its own HBM */
+B200SPMV_API int b200spmv_mg_convert_synth(b200spmv_mg *m, int kind, long long p0, long long p1, unsigned long long seed);
+/* host semantics, = SpMV(A_opt, x_opt, y): scatter x to the GPUs, exchange + multiply, gather y, synchronise */
+B200SPMV_API int b200spmv_mg_multiply_host(b200spmv_mg *m, const double *x_h, double *y_h);
+/* device-resident vectors: upload x once, then each mg_multiply is exchange + multiply only (asynchronous) */
+B200SPMV_API int b200spmv_mg_upload_x(b200spmv_mg *m, const double *x_h);
+B200SPMV_API int b200spmv_mg_multiply(b200spmv_mg *m);
+B200SPMV_API int b200spmv_mg_synchronize(b200spmv_mg *m);
+B200SPMV_API int b200spmv_mg_download_y(b200spmv_mg *m, double *y_h);
+/* nGPU nRow nCol nNnz | halo_total (x entries crossing NVLink per multiply) | graphed | alg_bytes | launches */
+B200SPMV_API int b200spmv_mg_get_scalar(b200spmv_mg *m, const char *name, long long *out);
+B200SPMV_API int b200spmv_mg_get_bounds(b200spmv_mg *m, int *bounds_h /* nGPU + 1 */);
+
 typedef struct b200spmv_halo b200spmv_halo;
 /* coo holds rows [rowBegin,rowEnd) with GLOBAL ids; the block owns x[colBegin,colEnd).  In place:
  * rows become block-local and columns get the monotone local numbering

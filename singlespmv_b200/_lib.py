@@ -72,6 +72,17 @@ def _load():
     lib.b200spmv_recommend_format.argtypes = [C.POINTER(Stats), C.POINTER(Options)]
     lib.b200spmv_partition_rows.argtypes = [vp, ll, ip, ip, vp]
     lib.b200spmv_partition_synth.argtypes = [ip, ll, ll, ip, vp]
+    lib.b200spmv_mg_create.argtypes = [ip, ip, C.POINTER(Options), C.POINTER(vp)]
+    lib.b200spmv_mg_destroy.argtypes = [vp]
+    lib.b200spmv_mg_convert_coo_host.argtypes = [vp, ip, ip, ll, vp, vp, vp]
+    lib.b200spmv_mg_convert_synth.argtypes = [vp, ip, ll, ll, C.c_ulonglong]
+    lib.b200spmv_mg_multiply_host.argtypes = [vp, vp, vp]
+    lib.b200spmv_mg_upload_x.argtypes = [vp, vp]
+    lib.b200spmv_mg_multiply.argtypes = [vp]
+    lib.b200spmv_mg_synchronize.argtypes = [vp]
+    lib.b200spmv_mg_download_y.argtypes = [vp, vp]
+    lib.b200spmv_mg_get_scalar.argtypes = [vp, C.c_char_p, C.POINTER(ll)]
+    lib.b200spmv_mg_get_bounds.argtypes = [vp, vp]
     lib.b200spmv_halo_plan.argtypes = [C.POINTER(Coo), ip, ip, C.POINTER(vp), vp]
     lib.b200spmv_halo_info.argtypes = [vp, vp]
     lib.b200spmv_halo_cols.argtypes = [vp, vp, ll]

@@ -392,6 +392,7 @@ int b200spmv_get_scalar(b200spmv_matrix *m, const char *name, long long *out)
     if (n == "nCol") { *out = f->nCol; return B200SPMV_OK; }
     if (n == "nNnz") { *out = f->nnz; return B200SPMV_OK; }
     if (n == "format") { *out = m->format; return B200SPMV_OK; }
+    if (n == "has_rows") { *out = f->has_rows() ? 1 : 0; return B200SPMV_OK; }
     if (f->scalar(n, out)) return B200SPMV_OK;
     set_error("get_scalar: format %d has no scalar '%s'", m->format, name);
     return B200SPMV_ERR_INVALID;

@@ -137,19 +137,19 @@ static int cs_launch(const ChunkStream &c, const XT *x, XT *y, int rb, int re, i
     const size_t smem = (size_t)S * ((size_t)capI * 4 + (size_t)capV * sizeof(VT));
     auto kern = chunk_stream_kernel<VT, XT, AT, MAXL, TH, ACC>;
     static int sms = 0;
-    static std::map<size_t, int> per_sm;                        // occupancy of THIS instantiation by shared-memory size
-    if (!sms) {
-        int dev = 0;
-        B2_CUDA(cudaGetDevice(&dev));
-        B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    auto it = per_sm.find(smem);
+    // occupancy of THIS instantiation by (device, shared-memory size): the opt-in shared-memory attribute is per device
+    static std::map<std::pair<int, size_t>, int> per_sm;
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    if (!sms) B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const auto key = std::make_pair(dev, smem);
+    auto it = per_sm.find(key);
     if (it == per_sm.end()) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 200 * 1024)));
         int n = 0;
         B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TH, smem));
         if (n < 1) { set_error("row-chunk stream: %zu bytes of shared memory do not fit", smem); return B200SPMV_ERR_UNSUPPORTED; }
-        it = per_sm.emplace(smem, n).first;
+        it = per_sm.emplace(key, n).first;
     }
     const int perSm = env_b > 0 ? std::min(it->second, env_b) : it->second;
     const int chunk0 = rb / TH, nChunks = ceil_div(re, TH) - chunk0;

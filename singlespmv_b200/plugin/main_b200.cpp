@@ -114,6 +114,16 @@ int main (int argc, char **argv) {
             g_profile = std::vector<double>(10);
             double elapsed;
 #ifdef B200_DEVICE_RESIDENT
+            if (A_opt.mg) {                                               // several GPUs: wall clock around the asynchronous loop
+                B200Synchronize(A_opt);
+                elapsed = -GetTimeBySec();
+                for (int i = 0; i < loop; i++) SpMV(A_opt, x_opt, y);
+                B200Synchronize(A_opt);
+                elapsed += GetTimeBySec();
+                elapsed /= loop;
+                if (t == 0 || elapsed < minElapsedTime) { minElapsedTime = elapsed; g_best_profile = g_profile; }
+                continue;
+            }
             DRV_CUDA(cudaEventRecord(e0, (cudaStream_t)A_opt.stream));
             for (int i = 0; i < loop; i++) SpMV(A_opt, x_opt, y);
             DRV_CUDA(cudaEventRecord(e1, (cudaStream_t)A_opt.stream));
@@ -169,7 +179,11 @@ int main (int argc, char **argv) {
     printf("%25s\t%d\n", "nCol", nCol);
     printf("%25s\t%d\n", "nNnz", nNnz);
     printf("%25s\t%d\n", "nThread", 1);                                   // host threads driving the device (src/main.cpp:200-206)
-    printf("%25s\t%d\n", "nGPU", 1);
+    printf("%25s\t%d\n", "nGPU", A_opt.nGPU);
+    if (A_opt.mg) {
+        printf("%25s\t%lld\n", "HaloDoublesPerSpMV", B200Scalar(A_opt, "halo_total"));
+        printf("%25s\t%lld\n", "GraphLaunch", B200Scalar(A_opt, "graphed"));
+    }
     printf("%25s\t%lf\n", "KernelTime(us)", minElapsedTime * 1e6);
     printf("%25s\t%lld\n", "AlgBytes", algBytes);
     printf("%25s\t%lf\n", "EffectiveBW(GB/s)", gbs);

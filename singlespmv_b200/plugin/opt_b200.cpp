@@ -52,6 +52,9 @@ void OptimizeProblem (const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_o
     A_opt.nNnz = A.nNnz;
     A_opt.x_dev = A_opt.y_dev = NULL;
     A_opt.stream = NULL;
+    A_opt.handle = NULL;
+    A_opt.mg = NULL;
+    A_opt.nGPU = 1;
     b200spmv_options opt = b200spmv_options();
     opt.segment_width = SEGMENT_WIDTH;
     opt.n_block = N_BLOCK;
@@ -65,9 +68,25 @@ void OptimizeProblem (const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_o
     opt.profile = 1;                // per-phase times -> g_profile[0] (Mul), g_profile[1] (Sum), src/opt_ss.cpp:225-304
 #endif
 #endif
+#ifdef B200_NGPU
+    {   // one process, several GPUs: row blocks by non-zero balance, x halo pulled over NVLink (include/b200spmv.h, mg)
+        int n = B200_NGPU;
+        if (getenv("B200_NGPU")) n = atoi(getenv("B200_NGPU"));
+        if (n <= 0) b200_check(b200spmv_device_count(&n), "device_count");
+        A_opt.nGPU = n;
+        b200_check(b200spmv_mg_create(n, B200_FORMAT_ENUM, &opt, &A_opt.mg), "mg_create");
+        b200_check(b200spmv_mg_convert_coo_host(A_opt.mg, A.nRow, A.nCol, A.nNnz, A.row_idx, A.col_idx, A.val), "mg_convert");
+#ifdef B200_DEVICE_RESIDENT
+        B200UploadVector(A_opt, x_opt);
+#else
+        if (!getenv("B200_NO_HOST_REGISTER") && x.size > 0) b200spmv_host_register(x.val, sizeof(double) * (unsigned long long)x.size);
+#endif
+        return;
+    }
+#endif
     b200_check(b200spmv_create(B200_FORMAT_ENUM, &opt, &A_opt.handle), "create");
     b200_check(b200spmv_convert_coo_host(A_opt.handle, A.nRow, A.nCol, A.nNnz, A.row_idx, A.col_idx, A.val), "convert");
-    if (B200_FORMAT_ENUM == B200SPMV_SS) {          // src/opt_ss.cpp:143-147: one count per fold step for the report
+    if (B200_FORMAT_ENUM == B200SPMV_SS && A_opt.handle) {          // src/opt_ss.cpp:143-147: one count per fold step for the report
         const long long bytes = b200spmv_get_array(A_opt.handle, "sum_segs_count", NULL, 0);
         g_step_count.assign(bytes > 0 ? (size_t)bytes / sizeof(int) : 0, 0);
         if (bytes > 0) b200spmv_get_array(A_opt.handle, "sum_segs_count", g_step_count.data(), bytes);
@@ -89,6 +108,15 @@ void OptimizeProblem (const SpMat &A, const Vec &x, SpMatOpt &A_opt, VecOpt &x_o
 
 extern "C" {
 void SpMV (const SpMatOpt &A, const VecOpt &x, Vec &y) {
+    if (A.mg) {
+#ifdef B200_DEVICE_RESIDENT
+        (void)x; (void)y;
+        b200_check(b200spmv_mg_multiply(A.mg), "mg_multiply");
+#else
+        b200_check(b200spmv_mg_multiply_host(A.mg, x.val, y.val), "mg_multiply_host");
+#endif
+        return;
+    }
 #ifdef B200_DEVICE_RESIDENT
     (void)x; (void)y;
     b200_check(b200spmv_multiply(A.handle, A.x_dev, A.y_dev, A.stream), "multiply");
@@ -114,17 +142,28 @@ void SpMV (const SpMatOpt &A, const VecOpt &x, Vec &y) {
 }
 
 void B200UploadVector (const SpMatOpt &A, const VecOpt &x) {
+    if (A.mg) { b200_check(b200spmv_mg_upload_x(A.mg, x.val), "mg_upload_x"); return; }
     if (!A.x_dev) return;
     b200_cuda(cudaMemcpy(A.x_dev, x.val, sizeof(double) * A.nCol, cudaMemcpyHostToDevice), "H2D x");
 }
 void B200FetchResult (const SpMatOpt &A, Vec &y) {
+    if (A.mg) {
+#ifdef B200_DEVICE_RESIDENT
+        b200_check(b200spmv_mg_download_y(A.mg, y.val), "mg_download_y");
+#endif
+        return;
+    }
     if (!A.y_dev) return;
     b200_cuda(cudaStreamSynchronize((cudaStream_t)A.stream), "sync");
     b200_cuda(cudaMemcpy(y.val, A.y_dev, sizeof(double) * A.nRow, cudaMemcpyDeviceToHost), "D2H y");
 }
-void B200Synchronize (const SpMatOpt &A) { b200_cuda(cudaStreamSynchronize((cudaStream_t)A.stream), "sync"); }
+void B200Synchronize (const SpMatOpt &A) {
+    if (A.mg) { b200_check(b200spmv_mg_synchronize(A.mg), "mg_synchronize"); return; }
+    b200_cuda(cudaStreamSynchronize((cudaStream_t)A.stream), "sync");
+}
 long long B200Scalar (const SpMatOpt &A, const char *name) {
     long long v = 0;
-    b200_check(b200spmv_get_scalar(A.handle, name, &v), name);
+    if (A.mg) b200_check(b200spmv_mg_get_scalar(A.mg, name, &v), name);
+    else b200_check(b200spmv_get_scalar(A.handle, name, &v), name);
     return v;
 }

@@ -11,6 +11,8 @@
 //     [-DB200_VALUE_F32]                  (CRS: matrix values stored as fp32, arithmetic in fp64)
 //     [-DB200_SS_FAITHFUL [-DPROFILING]]  (SS / CSS: the reference's three-phase schedule; with PROFILING the Mul and
 //                                          Sum phase times go to g_profile[0] / [1] like src/opt_ss.cpp:225-304)
+//     [-DB200_NGPU=N]                     (row-partition the matrix over N GPUs of the box, one process: b200spmv_mg_*;
+//                                          N = 0: all visible GPUs; the environment variable B200_NGPU overrides)
 //     [-DB200_DEVICE_RESIDENT]            (x stays in HBM, y is copied back only by B200FetchResult();
 //                                          default = host semantics like src/opt_cusparse.cpp:72-82)
 //
@@ -26,6 +28,8 @@ struct SpMatOpt {
     int nCol;
     int nNnz;
     b200spmv_matrix *handle;    // the converted matrix lives in HBM behind the C-ABI
+    b200spmv_mg *mg;            // -DB200_NGPU: the same matrix row-partitioned over several GPUs (handle is NULL then)
+    int nGPU;
     double *x_dev;              // device-resident mode only
     double *y_dev;
     void *stream;               // cudaStream_t used by the multiply (NULL = default stream)

@@ -36,6 +36,19 @@ def main():
         for _ in range(2):
             eng.step()
         torch.cuda.synchronize()
+        # host-semantics step (x slice from pinned host memory in pieces, y back in chunks): same bits as the device step
+        y_dev = eng.block.y.clone()
+        x_pin = torch.from_numpy(x_h[lo:hi].copy()).pin_memory()
+        y_pin = torch.full((hi - lo,), float("nan"), dtype=torch.float64).pin_memory()
+        eng.plan_host(max_chunks=5)
+        eng.block.x_owned.zero_()
+        for _ in range(2):
+            eng.step_host(x_pin, y_pin)
+        torch.cuda.synchronize()
+        host_ok = bool(torch.equal(y_pin, y_dev.cpu()))
+        flag_h = torch.tensor([1 if host_ok else 0], device="cuda")
+        dist.all_reduce(flag_h, op=dist.ReduceOp.MIN)
+        host_ok = bool(flag_h.item())
         sizes = [int(eng.bounds[r + 1] - eng.bounds[r]) for r in range(world)]
         parts = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
         dist.all_gather(parts, eng.block.y)
@@ -49,10 +62,10 @@ def main():
             torch.cuda.synchronize()
             same = bool(torch.equal(y, y1))
             halo = eng.block.nLeft + eng.block.nRight
-            print("dist_check %s p0=%d world=%d rows=%d halo(rank0)=%d interior(rank0)=[%d,%d) bit-identical=%s graph=%s %s"
-                  % (kind, p0, world, n, halo, eng.block.interiorBegin, eng.block.interiorEnd, same, graphed,
+            print("dist_check %s p0=%d world=%d rows=%d halo(rank0)=%d interior(rank0)=[%d,%d) bit-identical=%s host-step=%s graph=%s %s"
+                  % (kind, p0, world, n, halo, eng.block.interiorBegin, eng.block.interiorEnd, same, host_ok, graphed,
                      eng.graph_error or ""), flush=True)
-            ok = ok and same
+            ok = ok and same and host_ok
         dist.barrier()
         eng.release_graph()
         torch.cuda.synchronize()

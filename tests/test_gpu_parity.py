@@ -982,3 +982,70 @@ def test_fp32_full_size_c5(sp):
         A.destroy()
         B.destroy()
     d.free()
+
+
+# ------------------------------------------------------------------------------------------ one process, several GPUs (b200spmv_mg_*)
+def _mg_counts(sp):
+    n = sp.device_count()
+    return [g for g in (1, 2, 3, 4, 8) if g <= n]
+
+
+@pytest.mark.parametrize("fmt", ["crs", "ell", "jds"])
+def test_mg_matches_single_gpu(sp, oracle, fmt):
+    """b200spmv_mg_*: any host COO is split by non-zero balance over the GPUs of the box (as many as are visible; one
+    on the driver's box, where the path degenerates to a single block without halo), columns renumbered monotonically
+    -> y bit-identical to the single-GPU result of the same format and to the reference CRS result, through the host
+    entry, the device-resident entries and repeated (graph-launched) steps."""
+    from singlespmv_b200.mg import MgSpMat
+    mats = []
+    nr, nc, row, col, val = oracle.stencil("lap3d7", 30)
+    mats.append(("lap3d7", nr, nc, row, col, val))
+    nr, nc, row, col, val = oracle.rmat(42, 12, 90000)                   # halo = most of x: the all-gather-like case
+    mats.append(("rmat", nr, nc, row, col, val))
+    rng = np.random.default_rng(3)
+    row, col, val = skewed_matrix(rng, 3000, 3000, 9)                    # empty rows, long rows
+    mats.append(("skew", 3000, 3000, row, col, val))
+    for name, nRow, nCol, row, col, val in mats:
+        x = oracle.reference_vectors(nCol, nRow)[0]
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        if fmt == "ell" and name != "lap3d7":
+            continue
+        _, y1 = run_host(sp, fmt, nRow, nCol, row, col, val, x)
+        for g in _mg_counts(sp):
+            M = MgSpMat(g, fmt).convert_host(sp.SpMat(nRow, nCol, row, col, val))
+            b = M.bounds()
+            assert b[0] == 0 and b[-1] == nRow and np.all(np.diff(b) >= 0)
+            assert M.scalar("nNnz") == len(row) and M.scalar("nGPU") == g
+            y = np.full(nRow, np.nan)
+            M.multiply_host(x, y)
+            short = np.diff(np.searchsorted(row, np.arange(nRow + 1))) <= 64
+            assert np.array_equal(y[short], y_ref[short]), (name, g)
+            assert_y(y, y_ref, row, col, val, x, nRow)
+            if name != "rmat":
+                assert np.array_equal(y, y1), (name, g)
+            x2 = x[::-1].copy()
+            M.upload_x(x2)
+            for _ in range(3):
+                M.multiply()
+            y2 = np.full(nRow, np.nan)
+            M.download_y(y2)
+            assert_y(y2, oracle.crs_result(nRow, row, col, val, x2), row, col, val, x2, nRow)
+            if g > 1:
+                assert M.scalar("halo_total") > 0
+            M.destroy()
+
+
+def test_mg_synthetic_blocks(sp, oracle):
+    from singlespmv_b200.mg import MgSpMat
+    nr, nc, row, col, val = oracle.stencil("box3d27", 20)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    for g in _mg_counts(sp):
+        M = MgSpMat(g, "crs").convert_synth("box3d27", 20)
+        y = np.full(nr, np.nan)
+        M.multiply_host(x, y)
+        assert np.array_equal(y, y_ref), g
+        assert M.scalar("alg_bytes") == 12 * len(row) + 4 * (nr + g) + 16 * nr
+        M.destroy()
+    with pytest.raises(sp.B200SpmvError):
+        MgSpMat(64, "crs")                                               # more GPUs than the box has
