@@ -45,7 +45,8 @@ struct MgBlock {
     int *pull_owner = nullptr, *pull_idx = nullptr;
     const double **peer_x = nullptr;
     cudaStream_t compute = nullptr, comm = nullptr;
-    cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_done = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_halo = nullptr, ev_done = nullptr;            // eager steps: cross-stream / cross-step ordering
+    cudaEvent_t cev_halo = nullptr, cev_join = nullptr;                          // recorded only inside the graph capture
     double *x_owned() const { return x_ext + nLeft; }
 };
 
@@ -82,7 +83,7 @@ static void mg_release(b200spmv_mg *m)
         if (b.peer_x) cudaFree((void *)b.peer_x);
         if (b.compute) cudaStreamDestroy(b.compute);
         if (b.comm) cudaStreamDestroy(b.comm);
-        for (cudaEvent_t e : {b.ev_x, b.ev_halo, b.ev_done, b.ev_join}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {b.ev_x, b.ev_halo, b.ev_done, b.cev_halo, b.cev_join}) if (e) cudaEventDestroy(e);
     }
     m->blk.clear();
     m->converted = false;
@@ -101,7 +102,7 @@ static int mg_finish_blocks(b200spmv_mg *m, std::vector<b200spmv_coo> &coos)
         MG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         MG_CUDA(cudaStreamCreateWithPriority(&b.compute, cudaStreamNonBlocking, lo));
         MG_CUDA(cudaStreamCreateWithPriority(&b.comm, cudaStreamNonBlocking, hi));   // the small pull kernel must not queue behind the interior rows
-        for (cudaEvent_t *e : {&b.ev_x, &b.ev_halo, &b.ev_done, &b.ev_join}) MG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t *e : {&b.ev_x, &b.ev_halo, &b.ev_done, &b.cev_halo, &b.cev_join}) MG_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         b200spmv_coo &c = coos[(size_t)g];
         b.nnz = c.nnz;
         B2_TRY(b200spmv_halo_plan(&c, b.rowBegin, b.rowEnd, &b.halo, nullptr));
@@ -160,7 +161,8 @@ static int mg_finish_blocks(b200spmv_mg *m, std::vector<b200spmv_coo> &coos)
 }
 
 // enqueue one step on every GPU's streams.  captured = inside the graph capture: consecutive graph launches are
-// serialised as a whole, so the cross-step ordering events are not needed (and must not be waited on: not captured)
+// serialised as a whole, so the cross-step ordering events are not needed; the capture uses its own events (an event
+// recorded during capture cannot be waited on by ordinary stream work afterwards)
 static int mg_enqueue_step(b200spmv_mg *m, bool captured)
 {
     for (auto &b : m->blk) {
@@ -174,7 +176,7 @@ static int mg_enqueue_step(b200spmv_mg *m, bool captured)
             mg_pull_kernel<<<ceil_div(nHalo, 256), 256, 0, b.comm>>>(b.peer_x, b.pull_owner, b.pull_idx, nHalo, b.nLeft, b.nLocal, b.x_ext);
             B2_KERNEL_CHECK();
         }
-        MG_CUDA(cudaEventRecord(b.ev_halo, b.comm));
+        MG_CUDA(cudaEventRecord(captured ? b.cev_halo : b.ev_halo, b.comm));
     }
     for (auto &b : m->blk) {
         MG_CUDA(cudaSetDevice(b.dev));
@@ -182,14 +184,14 @@ static int mg_enqueue_step(b200spmv_mg *m, bool captured)
         if (!captured) MG_CUDA(cudaStreamWaitEvent(b.compute, b.ev_x, 0));
         if (b.interiorEnd > b.interiorBegin) {
             B2_TRY(b200spmv_multiply_rows(b.A, b.interiorBegin, b.interiorEnd, b.x_ext, b.y, b.compute));     // overlaps the pull
-            MG_CUDA(cudaStreamWaitEvent(b.compute, b.ev_halo, 0));
+            MG_CUDA(cudaStreamWaitEvent(b.compute, captured ? b.cev_halo : b.ev_halo, 0));
             if (b.interiorBegin > 0) B2_TRY(b200spmv_multiply_rows(b.A, 0, b.interiorBegin, b.x_ext, b.y, b.compute));
             if (b.interiorEnd < nRows) B2_TRY(b200spmv_multiply_rows(b.A, b.interiorEnd, nRows, b.x_ext, b.y, b.compute));
         } else {
-            MG_CUDA(cudaStreamWaitEvent(b.compute, b.ev_halo, 0));
+            MG_CUDA(cudaStreamWaitEvent(b.compute, captured ? b.cev_halo : b.ev_halo, 0));
             B2_TRY(b200spmv_multiply(b.A, b.x_ext, b.y, b.compute));
         }
-        MG_CUDA(cudaEventRecord(b.ev_done, b.compute));
+        if (!captured) MG_CUDA(cudaEventRecord(b.ev_done, b.compute));
     }
     return B200SPMV_OK;
 }
@@ -215,9 +217,9 @@ static int mg_capture(b200spmv_mg *m)
     for (auto &b : m->blk) {                                   // ... and is joined back into the origin stream
         if (!ok) break;
         cudaSetDevice(b.dev);
-        ok = cudaEventRecord(b.ev_join, b.compute) == cudaSuccess;          // comm is already joined through ev_halo
+        ok = cudaEventRecord(b.cev_join, b.compute) == cudaSuccess;         // comm is already joined through cev_halo
         cudaSetDevice(root.dev);
-        if (ok && b.compute != root.compute) ok = cudaStreamWaitEvent(root.compute, b.ev_join, 0) == cudaSuccess;
+        if (ok && b.compute != root.compute) ok = cudaStreamWaitEvent(root.compute, b.cev_join, 0) == cudaSuccess;
     }
     cudaSetDevice(root.dev);
     const cudaError_t e = cudaStreamEndCapture(root.compute, &g);
@@ -366,10 +368,16 @@ int b200spmv_mg_upload_x(b200spmv_mg *m, const double *x_h)
 {
     B2_TRY(mg_ready(m, "mg_upload_x"));
     if (!x_h && m->nCol) { set_error("mg_upload_x: NULL x"); return B200SPMV_ERR_INVALID; }
+    if (m->graph) {                                            // every earlier step (graph launches on GPU 0's compute stream) is finished
+        B2_CUDA(cudaSetDevice(m->blk[0].dev));
+        B2_CUDA(cudaStreamSynchronize(m->blk[0].compute));
+    }
     for (auto &b : m->blk) {
         B2_CUDA(cudaSetDevice(b.dev));
-        B2_CUDA(cudaStreamWaitEvent(b.compute, b.ev_done, 0));
-        for (auto &p : m->blk) B2_CUDA(cudaStreamWaitEvent(b.compute, p.ev_halo, 0));     // nobody is still pulling from this slice
+        if (!m->graph) {
+            B2_CUDA(cudaStreamWaitEvent(b.compute, b.ev_done, 0));
+            for (auto &p : m->blk) B2_CUDA(cudaStreamWaitEvent(b.compute, p.ev_halo, 0));   // nobody is still pulling from this slice
+        }
         if (b.nLocal) B2_CUDA(cudaMemcpyAsync(b.x_owned(), x_h + b.rowBegin, sizeof(double) * (size_t)b.nLocal, cudaMemcpyHostToDevice, b.compute));
         B2_CUDA(cudaEventRecord(b.ev_x, b.compute));
     }

@@ -59,24 +59,19 @@ __device__ __forceinline__ void st_prod4(float *p, float a, float b, float c, fl
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
 }
 
-// TMA = true: the tile's col / val slices are brought into shared memory by two 1-D bulk copies issued by one thread
-// (cp.async.bulk, SASS UBLKCP) instead of through every thread's load pipeline.  An SM sustains about one L1-missing
-// sector per clock (profiles/r2_gather_ceiling.md); on gather-bound matrices the x gathers need all of that, so the
-// 12 B/nnz matrix stream is taken off it.  The products overwrite the staged values in place when the types allow.
+// A variant that brought the tile's col / val slices in by TMA bulk copies (to take the matrix stream off the SM's L1 miss
+// path, which the x gathers saturate on gather-bound matrices) was measured and removed: with bulk copies in flight the
+// x slice no longer stays L2-resident, whatever cache policy the copies carry (c2 4.4-7.4 ms against 2.9, profiles/r2_experiments.md).
 // VT = stored value type, XT = type of x and y, AT = type of the products and sums.
-template <typename VT, typename XT, typename AT, int TH, bool TMA>
+template <typename VT, typename XT, typename AT, int TH>
 __global__ void __launch_bounds__(TH)
 tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
                    const VT *__restrict__ val, const int *__restrict__ tile_row,
                    const XT *__restrict__ x, XT *__restrict__ y, double *__restrict__ carry,
-                   int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok, int tma_policy)
+                   int nnz, int tileLo, int rowLo, int rowHi, int accumulate, int vec_ok)
 {
     constexpr int TILE = TH * TS_IPT;
-    constexpr bool INPLACE = sizeof(VT) == sizeof(AT);
     __shared__ __align__(16) AT prod[TILE];
-    __shared__ __align__(16) int scol[TMA ? TILE : 4];
-    __shared__ __align__(16) VT sval_own[(TMA && !INPLACE) ? TILE : 4];      // values that cannot share prod's slots
-    __shared__ __align__(8) uint64_t bar;
     __shared__ int long_row[TILE / TS_LONG + 2];
     __shared__ int n_long;
 
@@ -89,61 +84,7 @@ tile_stream_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col,
     if (tid == 0) n_long = 0;
 
     // ---- phase 1: stream the tile, gather x, park products in shared memory
-    if (TMA) {
-        VT *sval = INPLACE ? reinterpret_cast<VT *>(prod) : sval_own;
-        const int n = t1 - t0;
-        if (tid == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t bytesI = (uint32_t)((n * 4 + 15) & ~15), bytesV = (uint32_t)((n * (int)sizeof(VT) + 15) & ~15);
-            mbar_expect_tx(&bar, bytesI + bytesV);
-            if (tma_policy == 2) {                      // experiment: no L2 hint at all
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(scol)), "l"(col + t0), "r"(bytesI), "r"(smem_u32(&bar)) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(sval)), "l"(val + t0), "r"(bytesV), "r"(smem_u32(&bar)) : "memory");
-            } else {
-                uint64_t pol = pol_stream;
-                if (tma_policy == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-                if (tma_policy == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
-                tma_load_1d(scol, col + t0, bytesI, &bar, pol);
-                tma_load_1d(sval, val + t0, bytesV, &bar, pol);
-            }
-        }
-        mbar_wait(&bar, 0);
-        if (n == TILE) {
-            XT xs[TS_IPT];
-            int4 c[TS_IPT / 4];
-#pragma unroll
-            for (int k = 0; k < TS_IPT / 4; k++) c[k] = *reinterpret_cast<const int4 *>(scol + 4 * (tid + k * TH));
-#pragma unroll
-            for (int k = 0; k < TS_IPT / 4; k++) {
-                xs[4 * k + 0] = ld_x(x + c[k].x, pol_x);
-                xs[4 * k + 1] = ld_x(x + c[k].y, pol_x);
-                xs[4 * k + 2] = ld_x(x + c[k].z, pol_x);
-                xs[4 * k + 3] = ld_x(x + c[k].w, pol_x);
-            }
-#pragma unroll
-            for (int k = 0; k < TS_IPT / 4; k++) {
-                const int o = 4 * (tid + k * TH);
-                VT vv[4];
-                if (sizeof(VT) == 8) {
-                    *reinterpret_cast<double2 *>(vv) = *reinterpret_cast<const double2 *>(sval + o);
-                    *reinterpret_cast<double2 *>(vv + 2) = *reinterpret_cast<const double2 *>(sval + o + 2);
-                } else {
-                    *reinterpret_cast<float4 *>(vv) = *reinterpret_cast<const float4 *>(sval + o);
-                }
-                const AT v0 = (AT)vv[0], v1 = (AT)vv[1], v2 = (AT)vv[2], v3 = (AT)vv[3];
-                st_prod4(prod + o, Arith<AT>::mul(v0, (AT)xs[4 * k]), Arith<AT>::mul(v1, (AT)xs[4 * k + 1]),
-                         Arith<AT>::mul(v2, (AT)xs[4 * k + 2]), Arith<AT>::mul(v3, (AT)xs[4 * k + 3]));
-            }
-        } else {
-            for (int i = tid; i < n; i += TH) {
-                const AT v = (AT)sval[i];
-                prod[i] = Arith<AT>::mul(v, (AT)ld_x(x + scol[i], pol_x));
-            }
-        }
-    } else if (t1 - t0 == TILE && vec_ok) {
+    if (t1 - t0 == TILE && vec_ok) {
         int4 c[TS_IPT / 4];
         double2 v[TS_IPT / 2];
 #pragma unroll
@@ -263,8 +204,6 @@ int TileStream::build(const int *row_ptr_d, const int *col_d, const void *val_d,
     nnz = nnz_;
     static const int env_threads = getenv("B200SPMV_TS_THREADS") ? atoi(getenv("B200SPMV_TS_THREADS")) : 256;
     threads = (env_threads == 128 || env_threads == 512) ? env_threads : 256;
-    static const char *env_load = getenv("B200SPMV_TS_LOAD");           // "ldg" / "tma": how the tile's slices are read
-    if (env_load) tma = !strcmp(env_load, "tma");
     tile = threads * TS_IPT;
     nTiles = ceil_div(nnz, tile);
     B2_TRY(tile_row.alloc((size_t)nTiles + 1));
@@ -325,26 +264,10 @@ static int ts_launch(const TileStream &T, const XT *x, XT *y, int acc, int rowLo
     const int vec_ok = ((reinterpret_cast<uintptr_t>(T.col) | reinterpret_cast<uintptr_t>(T.val)) & 15) == 0;
     const int nT = tileHi - tileLo;
     const bool fix = nT > 1 || tileLo > 0;
-    // bulk copies need 16-byte aligned slices and may read up to 15 bytes past the last entry (callers keep CS_SLACK)
-    const bool use_tma = T.tma && vec_ok && T.threads <= 256;
-    static bool carveout_set = false;
-    if (use_tma && !carveout_set) {       // 8 resident CTAs x 24.7 KB: ask for the large shared-memory split once
-        carveout_set = true;
-        cudaFuncSetAttribute(tile_stream_kernel<VT, XT, AT, 256, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(tile_stream_kernel<VT, XT, AT, 128, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaGetLastError();
-    }
-    static const int tma_policy = getenv("B200SPMV_TMA_POLICY") ? atoi(getenv("B200SPMV_TMA_POLICY")) : 0;
-#define TS_ARGS T.row_ptr, T.col, v, T.tile_row.p, x, y, T.carry.p, T.nnz, tileLo, rowLo, rowHi, acc, vec_ok, tma_policy
-    if (T.threads == 128) {
-        if (use_tma) tile_stream_kernel<VT, XT, AT, 128, true><<<nT, 128, 0, s>>>(TS_ARGS);
-        else tile_stream_kernel<VT, XT, AT, 128, false><<<nT, 128, 0, s>>>(TS_ARGS);
-    } else if (T.threads == 512) {
-        tile_stream_kernel<VT, XT, AT, 512, false><<<nT, 512, 0, s>>>(TS_ARGS);
-    } else {
-        if (use_tma) tile_stream_kernel<VT, XT, AT, 256, true><<<nT, 256, 0, s>>>(TS_ARGS);
-        else tile_stream_kernel<VT, XT, AT, 256, false><<<nT, 256, 0, s>>>(TS_ARGS);
-    }
+#define TS_ARGS T.row_ptr, T.col, v, T.tile_row.p, x, y, T.carry.p, T.nnz, tileLo, rowLo, rowHi, acc, vec_ok
+    if (T.threads == 128) tile_stream_kernel<VT, XT, AT, 128><<<nT, 128, 0, s>>>(TS_ARGS);
+    else if (T.threads == 512) tile_stream_kernel<VT, XT, AT, 512><<<nT, 512, 0, s>>>(TS_ARGS);
+    else tile_stream_kernel<VT, XT, AT, 256><<<nT, 256, 0, s>>>(TS_ARGS);
 #undef TS_ARGS
     if (fix)
         tile_fixup_kernel<VT, XT, AT><<<ceil_div(nT, 256), 256, 0, s>>>(T.row_ptr, T.col, v, T.tile_row.p, x, y, T.carry.p, tileLo,

@@ -44,7 +44,6 @@ struct TileStream {
     // owned
     int nTiles = 0;
     int threads = TS_THREADS, tile = TS_TILE;   // CTA width and entries per tile of this instance
-    bool tma = false;               // tile slices arrive by TMA bulk copy instead of through the threads' loads
     DevBuf<int> tile_row;           // [nTiles+1]: first row whose first entry is >= tile start
     DevBuf<double> carry;           // [nTiles]
 
