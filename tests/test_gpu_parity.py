@@ -1038,7 +1038,7 @@ def test_mg_matches_single_gpu(sp, oracle, fmt):
             short = np.diff(np.searchsorted(row, np.arange(nRow + 1))) <= 64
             assert np.array_equal(y[short], y_ref[short]), (name, g)
             assert_y(y, y_ref, row, col, val, x, nRow)
-            if name != "rmat":
+            if name == "lap3d7":                                     # rows of one thread each: partitioning cannot change a bit
                 assert np.array_equal(y, y1), (name, g)
             x2 = x[::-1].copy()
             M.upload_x(x2)
