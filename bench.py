@@ -47,9 +47,9 @@ WORKLOADS = {
                name="sliced-ELL / SS / JDS fp64, uniform random 16,777,216 rows x 32 nnz/row (536,870,912 nnz)"),
     "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="csr5", formats=["csr5", "crs"], cusparse=True, f32=["crs"],
                name="CSR5-style and adaptive CRS fp64, R-MAT scale 23, 2^28 edge draws (duplicates removed)"),
-    "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia", formats=["dia", "ell", "crs"], f32=["ell"],
+    "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia", formats=["dia", "ell", "crs"], f32=["dia", "ell"],
                name="DIA fp64, 3-D 27-point stencil 256^3 (16,777,216 rows, 449,455,096 nnz)"),
-    "c5": dict(kind="lap3d7", p0=512, p1=0, seed=1, fmt="crs", cusparse=True, f32=["crs", "ell"],
+    "c5": dict(kind="lap3d7", p0=512, p1=0, seed=1, fmt="crs", cusparse=True, f32=["crs", "ell", "dia"],
                formats=["crs", "dia", "ell", "jds", "ss", "css", "csr5", "coo"],
                name="row-partitioned CRS fp64, 3-D 7-point Laplacian 512^3 (134,217,728 rows, 937,951,232 nnz)"),
 }
@@ -57,9 +57,9 @@ MINI = {"c1": dict(p0=128), "c2": dict(p0=1 << 16), "c3": dict(p0=14, p1=1 << 18
         "c5": dict(p0=64)}
 HEADLINE = "c5"
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
-# captures (profiles/r1_ncu_kernels.md, profiles/r2_ncu_kernels.md).  Keyed by (workload, format); anything else null.
-NCU_TRAFFIC = {("c2", "css"): 2415011680, ("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE multiply's launches of the dominant kernel, from the committed
+# ncu --set full captures (profiles/r1_ncu_kernels.md, profiles/r2_ncu_kernels.md).  Keyed by (workload, format); else null.
+NCU_TRAFFIC = {("c2", "css"): 3 * 2415011680, ("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
                ("c4", "dia"): 3870562096, ("c4", "ell"): 5853024560, ("c5", "dia"): 9634725000,
                ("c5", "csr5"): 13638726000, ("c5", "coo"): 20025184000}
 try:                                    # captures of this round's kernels, written by scripts/ncu_traffic.py
@@ -432,7 +432,8 @@ def run_case(sp, torch, timer, wl_key, wl, fmt, options, coo, x_d, y_d, sptr, st
     e = {"format": fmt, "options": {k: v for k, v in options.items() if v}, "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9,
          "ms_per_step": ms, "alg_bytes": alg_bytes, "alg_gbs": alg_bytes / (ms * 1e-3) / 1e9,
          "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "frac_of_8000": alg_bytes / (ms * 1e-3) / 1e9 / 8000.0,
-         "traffic": None if mini else NCU_TRAFFIC.get((wl_key, fmt)), "launches_per_step": A.scalar("launches"),
+         "traffic": None if mini else NCU_TRAFFIC.get((wl_key, fmt + ("_f32" if options.get("precision") else ""))),
+         "launches_per_step": A.scalar("launches"),
          "convert_ms": t_conv * 1e3, "l2": "flushed between steps" if cold else "streams more than L2"}
     if cold:
         e["warm_l2_ms_per_step"] = timer.run(step, steps, 1, False)
@@ -563,6 +564,8 @@ def run_single(args, wl_key, only_format):
     sp.host_unregister(yh)
 
     dom_launches = A.scalar("nBlock") if fmt == "css" else 1
+    if fmt in ("ell", "jds", "ss"):
+        dom_launches = max(1, A.scalar("col_blocks"))        # column-block engine: one tile-stream launch per block
     line = {"metric": "SpMV GFLOP/s", "value": head["gflops"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if f32 else "f64", "data": "synthetic",
@@ -573,11 +576,13 @@ def run_single(args, wl_key, only_format):
                        "parallelism": "1 GPU (the N = 2/4/8 lines row-partition the same matrix: strong scaling)",
                        "convert_ms": head["convert_ms"], "generate_ms": t_gen * 1e3},
             "roofline": {"bound": "hbm", "achieved": head["alg_gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
-                         "frac_of_8000_nominal": head["frac_of_8000"], "traffic": head["traffic"], "peak_source": peak_src,
+                         "frac_of_8000_nominal": head["frac_of_8000"],
+                         "traffic": head["traffic"] // dom_launches if head["traffic"] else None, "peak_source": peak_src,
                          "kernel": DOMINANT.get(fmt, fmt), "alg_bytes_per_launch": alg_bytes // dom_launches,
                          "dominant_launches_per_step": dom_launches, "avg_launch_ms": ms / dom_launches,
                          "note": "achieved = alg_bytes_per_launch / avg_launch_ms (CUDA events over the timed region); "
-                                 "traffic = ncu dram read+write of one launch (profiles/)"},
+                                 "traffic = ncu dram read+write per launch (profiles/r2_ncu_kernels.md); `configs` entries carry "
+                                 "alg_bytes and traffic per multiply"},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": (4 if f32 else 8) * nCol, "d2h_bytes_per_step": (4 if f32 else 8) * nRow,
                     "host_buffers": "numpy arrays page-locked once by the plugin layer (cudaHostRegister), as "

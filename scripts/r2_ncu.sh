@@ -12,8 +12,8 @@ python bench.py --workload c5 $A > gpurun_out/plain_launches_c5.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches_c5_default.csv python bench.py --workload c5 $A > gpurun_out/ncu_launches_c5.log 2>&1; echo "launch list c5 rc=$?"
 python bench.py --workload c2 --format ell $A > gpurun_out/plain_launches_c2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches_c2_ell.csv python bench.py --workload c2 --format ell $A > gpurun_out/ncu_launches_c2.log 2>&1; echo "launch list c2 rc=$?"
-cap c5_crs chunk_stream_kernel 3 2 --workload c5 $A
-cap c1_crs chunk_stream_kernel 3 2 --workload c1 $A
+cap c5_crs chunk_stream_kernel 3 1 --workload c5 $A
+cap c1_crs chunk_stream_kernel 3 1 --workload c1 $A
 cap c2_ell tile_stream_kernel 9 3 --workload c2 --format ell $A
 cap c2_jds tile_stream_kernel 9 3 --workload c2 --format jds $A
 cap c3_crs tile_stream_kernel 3 1 --workload c3 --format crs $A

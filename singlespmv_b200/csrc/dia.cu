@@ -49,23 +49,25 @@ __global__ void dia_ioff_kernel(const int *__restrict__ flag, const int *__restr
     if (d < N && flag[d]) ioff[slot[d]] = d;                  // opt_dia.cpp:38-44
 }
 
+template <typename VT>
 __global__ void dia_scatter_kernel(const int *__restrict__ row, const int *__restrict__ col,
                                    const double *__restrict__ val, int nnz, int shift,
-                                   const int *__restrict__ slot, size_t ld, double *__restrict__ diag)
+                                   const int *__restrict__ slot, size_t ld, VT *__restrict__ diag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) diag[(size_t)slot[col[i] - row[i] + shift] * ld + row[i]] = val[i];   // opt_dia.cpp:52-54
+    if (i < nnz) diag[(size_t)slot[col[i] - row[i] + shift] * ld + row[i]] = (VT)val[i];   // opt_dia.cpp:52-54 (fp32 storage: rounded once)
 }
 
 // reference layout diag[p][col]: the entry of row col - off_p, zero where that row does not exist
-__global__ void dia_logical_kernel(const double *__restrict__ diag, size_t ld, const int *__restrict__ ioff,
+template <typename VT>
+__global__ void dia_logical_kernel(const VT *__restrict__ diag, size_t ld, const int *__restrict__ ioff,
                                    int nDiag, int nRow, int nCol, double *__restrict__ out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)nDiag * nCol) return;
     const int p = (int)(i / nCol), c = (int)(i % nCol);
     const int r = c + (nRow - 1) - ioff[p];
-    out[i] = (r >= 0 && r < nRow) ? diag[(size_t)p * ld + r] : 0.0;
+    out[i] = (r >= 0 && r < nRow) ? (double)diag[(size_t)p * ld + r] : 0.0;
 }
 
 // window of run g for the CTA starting at row0: columns [c_lo, c_hi), smem index = col - w0
@@ -222,11 +224,46 @@ dia_spmv_direct_kernel(const double *__restrict__ diag, size_t ld, int nDiag, co
     y[r] = acc;
 }
 
+// fp32 variant (options.precision): fp32 diagonals and vectors, x through L1 / L2 (coalesced: lane = row), sums in AT
+template <typename AT>
+__global__ void __launch_bounds__(DIA_THREADS)
+dia_spmv_f32_kernel(const float *__restrict__ diag, size_t ld, int nDiag, const int *__restrict__ ioff,
+                    const float *__restrict__ x, float *__restrict__ y, int nRow, int nCol)
+{
+    const int r = blockIdx.x * DIA_THREADS + threadIdx.x;
+    if (r >= nRow) return;
+    const uint64_t pol_x = policy_evict_last();
+    const int shift = nRow - 1;
+    AT acc = (AT)0;
+    int p = 0;
+    for (; p + 4 <= nDiag; p += 4) {
+        float d[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) d[u] = __ldcs(diag + (size_t)(p + u) * ld + r);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = r + ioff[p + u] - shift;
+            xv[u] = (c >= 0 && c < nCol) ? ld_x(x + c, pol_x) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)d[u], (AT)xv[u]));
+    }
+    for (; p < nDiag; p++) {
+        const int c = r + ioff[p] - shift;
+        const float xv = (c >= 0 && c < nCol) ? ld_x(x + c, pol_x) : 0.0f;
+        acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)__ldcs(diag + (size_t)p * ld + r), (AT)xv));
+    }
+    y[r] = (float)acc;
+}
+
 struct DiaFormat : Format {
     int nDiag = 0;
     size_t ld = 0;
     DevBuf<int> ioff;
     DevBuf<double> diag;
+    DevBuf<float> diag32;                 // options.precision = 1 / 2
+    int prec = 0;
+    explicit DiaFormat(const b200spmv_options &o) : prec(o.precision) {}
     DiaRuns runs{};
     int offMin = 0, offMax = 0;           // smallest / largest col - row over the stored diagonals
     bool tma_ok = false;
@@ -252,20 +289,26 @@ struct DiaFormat : Format {
         ld = ((size_t)nRow + 31) & ~(size_t)31;
         size_t freeB = 0, totalB = 0;
         B2_CUDA(cudaMemGetInfo(&freeB, &totalB));
-        if ((double)nDiag * (double)ld * 8.0 > (double)freeB * 0.95) {
+        if ((double)nDiag * (double)ld * (prec ? 4.0 : 8.0) > (double)freeB * 0.95) {
             set_error("DIA: %d diagonals x %d rows = %.1f GB do not fit the free %.1f GB of HBM (the reference "
                       "allocates the same dense slab, src/opt_dia.cpp:47-51)", nDiag, nRow, nDiag * (double)ld * 8e-9, freeB * 1e-9);
             return B200SPMV_ERR_NOMEM;
         }
         B2_TRY(ioff.alloc((size_t)nDiag));
-        B2_TRY(diag.alloc((size_t)nDiag * ld));
-        B2_CUDA(cudaMemsetAsync(diag.p, 0, diag.bytes(), s));
+        if (prec) {
+            B2_TRY(diag32.alloc((size_t)nDiag * ld));
+            B2_CUDA(cudaMemsetAsync(diag32.p, 0, diag32.bytes(), s));
+        } else {
+            B2_TRY(diag.alloc((size_t)nDiag * ld));
+            B2_CUDA(cudaMemsetAsync(diag.p, 0, diag.bytes(), s));
+        }
         if (N) {
             dia_ioff_kernel<<<ceil_div(N, 256), 256, 0, s>>>(flag.p, slot.p, N, ioff.p);
             B2_KERNEL_CHECK();
         }
         if (nnz) {
-            dia_scatter_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(A.row, A.col, A.val, nnz, shift, slot.p, ld, diag.p);
+            if (prec) dia_scatter_kernel<float><<<ceil_div(nnz, 256), 256, 0, s>>>(A.row, A.col, A.val, nnz, shift, slot.p, ld, diag32.p);
+            else dia_scatter_kernel<double><<<ceil_div(nnz, 256), 256, 0, s>>>(A.row, A.col, A.val, nnz, shift, slot.p, ld, diag.p);
             B2_KERNEL_CHECK();
         }
         // runs of consecutive diagonals share one x window
@@ -306,7 +349,18 @@ struct DiaFormat : Format {
     }
 
     int multiply(const double *x, double *y, cudaStream_t s) override { return multiply_rows(0, nRow, x, y, s); }
-    bool has_rows() const override { return true; }
+    int multiply_f32(const float *x, float *y, cudaStream_t s) override
+    {
+        if (!prec) { set_error("multiply_f32: the handle was created with precision = 0 (fp64 vectors)"); return B200SPMV_ERR_STATE; }
+        if (nRow == 0) return B200SPMV_OK;
+        if (nDiag == 0) { B2_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)nRow, s)); return B200SPMV_OK; }
+        const int grid = ceil_div(nRow, DIA_THREADS);
+        if (prec == 2) dia_spmv_f32_kernel<double><<<grid, DIA_THREADS, 0, s>>>(diag32.p, ld, nDiag, ioff.p, x, y, nRow, nCol);
+        else dia_spmv_f32_kernel<float><<<grid, DIA_THREADS, 0, s>>>(diag32.p, ld, nDiag, ioff.p, x, y, nRow, nCol);
+        B2_KERNEL_CHECK();
+        return B200SPMV_OK;
+    }
+    bool has_rows() const override { return !prec; }
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
@@ -319,6 +373,7 @@ struct DiaFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
+        if (prec) { set_error("multiply: the handle was created with precision = %d, use b200spmv_multiply_f32", prec); return B200SPMV_ERR_STATE; }
         if (rb == re) return B200SPMV_OK;
         if (nDiag == 0) {
             B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
@@ -347,10 +402,11 @@ struct DiaFormat : Format {
         if (n == "nRuns") { *out = runs.n; return true; }
         if (n == "tma") { *out = tma_ok ? 1 : 0; return true; }
         if (n == "alg_bytes") {   // 8 nDiag nCol + 4 nDiag + 8 nCol + 8 nRow
-            *out = 8LL * nDiag * nCol + 4LL * nDiag + 8LL * nCol + 8LL * nRow;
+            *out = (prec ? 4LL : 8LL) * ((long long)nDiag * nCol + nCol + nRow) + 4LL * nDiag;
             return true;
         }
         if (n == "launches") { *out = 1; return true; }
+        if (n == "precision") { *out = prec; return true; }
         return false;
     }
 
@@ -362,13 +418,14 @@ struct DiaFormat : Format {
             if (!dst) return (long long)(cnt * sizeof(double));
             DevBuf<double> out;
             if (out.alloc(cnt)) return B200SPMV_ERR_NOMEM;
-            if (cnt) dia_logical_kernel<<<ceil_div((long long)cnt, 256), 256>>>(diag.p, ld, ioff.p, nDiag, nRow, nCol, out.p);
+            if (cnt && prec) dia_logical_kernel<float><<<ceil_div((long long)cnt, 256), 256>>>(diag32.p, ld, ioff.p, nDiag, nRow, nCol, out.p);
+            else if (cnt) dia_logical_kernel<double><<<ceil_div((long long)cnt, 256), 256>>>(diag.p, ld, ioff.p, nDiag, nRow, nCol, out.p);
             return export_device(out.p, cnt * sizeof(double), dst, cap);
         }
         return -1000;
     }
 };
 
-Format *make_dia(const b200spmv_options &) { return new DiaFormat(); }
+Format *make_dia(const b200spmv_options &o) { return new DiaFormat(o); }
 
 }  // namespace b2
