@@ -45,7 +45,7 @@ WORKLOADS = {
     "c2": dict(kind="uniform", p0=1 << 24, p1=32, seed=1, fmt="ell", formats=["ell", "ss", "jds", "css"], f32=["ell", "crs"],
                fmt_opts={"css": dict(n_block=3)},
                name="sliced-ELL / SS / JDS fp64, uniform random 16,777,216 rows x 32 nnz/row (536,870,912 nnz)"),
-    "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="csr5", formats=["csr5", "crs"], cusparse=True, f32=["crs"],
+    "c3": dict(kind="rmat", p0=23, p1=1 << 28, seed=42, fmt="csr5", formats=["csr5", "crs"], cusparse=True, f32=["csr5", "crs"],
                name="CSR5-style and adaptive CRS fp64, R-MAT scale 23, 2^28 edge draws (duplicates removed)"),
     "c4": dict(kind="box3d27", p0=256, p1=0, seed=1, fmt="dia", formats=["dia", "ell", "crs"], f32=["dia", "ell"],
                name="DIA fp64, 3-D 27-point stencil 256^3 (16,777,216 rows, 449,455,096 nnz)"),

@@ -86,7 +86,7 @@ typedef struct {
                             blocks), n > 0 = force n column blocks, -1 = never.  The reference arrays (exports) and y
                             are the same either way: every row is still summed in ascending column order (rows of more
                             than 64 entries per block: within the 1e-12 tolerance) */
-    int precision;       /* CRS / ELL / DIA: 0 = fp64 (the reference); 1 = fp32: matrix values rounded once to fp32 at conversion,
+    int precision;       /* CRS / ELL / DIA / CSR5: 0 = fp64 (the reference); 1 = fp32: matrix values rounded once to fp32 at conversion,
                             x and y are float arrays, products and sums in fp32; 2 = the same storage and vectors with
                             fp64 products and sums.  Multiply with b200spmv_multiply_f32 / _host_f32; tolerance 1e-5
                             against the reference's (fp64) CRS result.  Halves the bytes of every array but the indices */

@@ -14,12 +14,14 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WANT = {"gpu__time_duration.sum": "dur", "dram__bytes_read.sum": "rd", "dram__bytes_write.sum": "wr",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "lts__t_sector_hit_rate.pct": "l2_hit",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "dram__bytes.sum.per_second": "dram_bps", "lts__t_sector_hit_rate.pct": "l2_hit",
         "l1tex__t_sector_hit_rate.pct": "l1_hit", "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
         "launch__registers_per_thread": "regs", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps",
         "launch__grid_size": "grid", "launch__block_size": "block",
         "sm__inst_executed_pipe_uniform.sum": "uni"}
-UNIT = {"nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+UNIT = {"nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
+        "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
+        "byte/s": 1.0, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}
 
 
 def rows_of(rep):
@@ -47,8 +49,8 @@ def main():
     traffic, lines = {}, ["# Round 2: `ncu --set full --clock-control none` captures of the dominant kernels (one B200)\n\n",
                           "Produced by `scripts/r2_ncu.sh` on the GPU box, read here with `scripts/ncu_traffic.py`.  Durations under ncu are\n",
                           "cold-cache and serialised: compare shares and byte counts, not times.  alg = compulsory bytes of the launch.\n\n",
-                          "| capture | kernel | launch | duration | DRAM read | DRAM write | DRAM % of peak | L2 % | L2 hit % | L1 hit % | regs | grid x block |\n",
-                          "|---|---|---|---|---|---|---|---|---|---|---|---|\n"]
+                          "| capture | kernel | launch | duration | DRAM read | DRAM write | DRAM GB/s | DRAM % of peak | L2 % | L2 hit % | L1 hit % | regs | grid x block |\n",
+                          "|---|---|---|---|---|---|---|---|---|---|---|---|---|\n"]
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "r2_prof_*.ncu-rep"))):
         tag = os.path.basename(rep)[len("r2_prof_"):-len(".ncu-rep")]
         rows = rows_of(rep)
@@ -57,9 +59,9 @@ def main():
         total = 0.0
         for i, d in enumerate(rows):
             total += d.get("rd", 0) + d.get("wr", 0)
-            lines.append("| %s | `%s` | %d | %.1f us | %.3f GB | %.3f GB | %.1f | %.1f | %.1f | %.1f | %d | %d x %d |\n" % (
+            lines.append("| %s | `%s` | %d | %.1f us | %.3f GB | %.3f GB | %.0f | %.1f | %.1f | %.1f | %.1f | %d | %d x %d |\n" % (
                 tag, re.sub(r"\(.*", "", d["kernel"])[:60], i, d.get("dur", 0) * 1e6, d.get("rd", 0) / 1e9, d.get("wr", 0) / 1e9,
-                d.get("dram_pct", 0), d.get("l2_pct", 0), d.get("l2_hit", 0), d.get("l1_hit", 0), int(d.get("regs", 0)),
+                d.get("dram_bps", 0) / 1e9, d.get("dram_pct", 0), d.get("l2_pct", 0), d.get("l2_hit", 0), d.get("l1_hit", 0), int(d.get("regs", 0)),
                 int(d.get("grid", 0)), int(d.get("block", 0))))
         m = re.match(r"(c\d)_([a-z0-9]+)(_f32)?$", tag)
         if m:

@@ -2,6 +2,8 @@
 bash scripts/r2_multi.sh 8 quick
 timeout 400 python tests/mg_check.py 8 2>&1 | tail -2
 timeout 300 python tests/mg_check.py 4 2>&1 | tail -1
+# global nnz beyond int32 (3.58 G), every block below it: the multi-GPU paths lift the reference's 2^31 ceiling (src/util.h:8)
+MG_CHECK_P0=800 MG_CHECK_NO_SINGLE=1 timeout 600 python tests/mg_check.py 8 2>&1 | tail -2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512"
 timeout 300 $TR bench.py --gpus 4 --steps 30 --warmup 5 --no-cpu > gpurun_out/r2_bench_multi_4.json 2> gpurun_out/r2_bench_multi_4.err; python - <<'PY'
 import json

@@ -127,8 +127,8 @@ int b200spmv_create(int format, const b200spmv_options *opts, b200spmv_matrix **
         return B200SPMV_ERR_UNSUPPORTED;
     }
     if (o.precision < 0 || o.precision > 2) { set_error("create: precision=%d (0 fp64, 1 fp32, 2 fp32 with fp64 sums)", o.precision); return B200SPMV_ERR_INVALID; }
-    if (o.precision && format != B200SPMV_CRS && format != B200SPMV_ELL && format != B200SPMV_DIA) {
-        set_error("create: the fp32 variant exists for the CRS, ELL and DIA formats");
+    if (o.precision && format != B200SPMV_CRS && format != B200SPMV_ELL && format != B200SPMV_DIA && format != B200SPMV_CSR5) {
+        set_error("create: the fp32 variant exists for the CRS, ELL, DIA and CSR5 formats");
         return B200SPMV_ERR_UNSUPPORTED;
     }
     Format *f = make_format(format, o);

@@ -141,8 +141,9 @@ __global__ void c5_offset_kernel(const int *__restrict__ row_ptr, const uint32_t
 }
 
 // (lane l, step i): l*sigma+i -> i*32+l inside full tiles whose raw tile_ptr differs from the next (format_avx2.h:366-420)
+template <typename VT>
 __global__ void c5_transpose_kernel(const int *__restrict__ col, const double *__restrict__ val, const uint32_t *__restrict__ tile_ptr,
-                                    int nnz, int sigma, int p, int *__restrict__ col_out, double *__restrict__ val_out)
+                                    int nnz, int sigma, int p, int *__restrict__ col_out, VT *__restrict__ val_out)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
@@ -153,15 +154,31 @@ __global__ void c5_transpose_kernel(const int *__restrict__ col, const double *_
         src = t * T + l * sigma + i;
     }
     col_out[k] = col[src];
-    val_out[k] = val[src];
+    val_out[k] = (VT)val[src];                       // fp32 storage (options.precision): rounded once, here
 }
 
 // ---------------------------------------------------------------- multiply
+// VT = stored value type, XT = type of x and y, AT = type of the products and segment sums (carries stay fp64)
+__device__ __forceinline__ double c5_ld_val(const double *p, uint64_t pol) { return ld_stream_d1(p, pol); }
+__device__ __forceinline__ float c5_ld_val(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename VT, typename XT, typename AT>
 __global__ void __launch_bounds__(C5_WARPS * 32)
-c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, const int *__restrict__ row_ptr,
+c5_compute_kernel(const int *__restrict__ col, const VT *__restrict__ val, const int *__restrict__ row_ptr,
                   const uint32_t *__restrict__ tile_ptr, const uint32_t *__restrict__ desc,
-                  const int *__restrict__ offset_ptr, const int *__restrict__ offset, const double *__restrict__ x,
-                  double *__restrict__ y, double *__restrict__ carry, int m, int sigma, int p, int bit_y, int bit_all,
+                  const int *__restrict__ offset_ptr, const int *__restrict__ offset, const XT *__restrict__ x,
+                  XT *__restrict__ y, double *__restrict__ carry, int m, int sigma, int p, int bit_y, int bit_all,
                   int num_packet, int nTileBlocks)
 {
     const int lane = threadIdx.x & 31;
@@ -174,10 +191,10 @@ c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, c
         const int r = r0 + ((int)blockIdx.x - nTileBlocks) * blockDim.x + threadIdx.x;
         if (r >= m) return;
         const int b = r == r0 ? (p - 1) * T : row_ptr[r], e = row_ptr[r + 1];
-        double acc = 0.0;
-        for (int j = b; j < e; j++) acc = __dadd_rn(acc, __dmul_rn(val[j], ld_x(x + col[j], pol_x)));
-        if (r == r0) carry[p - 1] = acc;       // the row may have started in an earlier tile
-        else y[r] = acc;
+        AT acc = (AT)0;
+        for (int j = b; j < e; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)val[j], (AT)ld_x(x + col[j], pol_x)));
+        if (r == r0) carry[p - 1] = (double)acc;       // the row may have started in an earlier tile
+        else y[r] = (XT)acc;
         return;
     }
 
@@ -186,14 +203,14 @@ c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, c
     const uint32_t ts = tile_ptr[t];
     const int start = (int)(ts & C5_MASK), stop = (int)(tile_ptr[t + 1] & C5_MASK);
     const int *c = col + (size_t)t * T + lane;
-    const double *v = val + (size_t)t * T + lane;
+    const VT *v = val + (size_t)t * T + lane;
 
     if (start == stop) {                       // fast track: the whole tile lies inside one row
-        double sum = 0.0;
+        AT sum = (AT)0;
         for (int i = 0; i < sigma; i++)
-            sum += ld_stream_d1(v + i * C5_OMEGA, pol_stream) * ld_x(x + ld_stream_i1(c + i * C5_OMEGA, pol_stream), pol_x);
+            sum += (AT)c5_ld_val(v + i * C5_OMEGA, pol_stream) * (AT)ld_x(x + ld_stream_i1(c + i * C5_OMEGA, pol_stream), pol_x);
         sum = warp_sum(sum);
-        if (lane == 0) carry[t] = sum;
+        if (lane == 0) carry[t] = (double)sum;
         return;
     }
 
@@ -203,25 +220,26 @@ c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, c
     uint32_t flags = c5_lane_flags(dt, lane, num_packet, bit_all, sigma);
     const bool starts_row = flags >> 31;       // a row starts at this lane's first entry
     if (lane == 0) flags |= 0x80000000u;       // csr5_spmv_cuda.h:138
-    double *yt = y + start + 1;
+    XT *yt = y + start + 1;
     const int *off = dirty ? offset + offset_ptr[t] : nullptr;
 
     if (dirty)                                  // beta = 0: rows without entries inside this tile's span
         for (int r = start + 1 + lane; r <= stop && r < m; r += 32)
-            if (row_ptr[r] == row_ptr[r + 1]) y[r] = 0.0;
+            if (row_ptr[r] == row_ptr[r + 1]) y[r] = (XT)0;
 
     // ---- thread-level segmented sums (csr5_spmv_cuda.h:141-176)
     bool direct = starts_row && lane != 0;
-    double sum = 0.0, first_sum = 0.0;
+    AT sum = (AT)0, first_sum = (AT)0;
     constexpr int CH = 4;                       // entries per lane in flight (8: 72 registers, 37 % occupancy in ncu)
     for (int i0 = 0; i0 < sigma; i0 += CH) {
         int cc[CH];
-        double vv[CH], xx[CH];
+        VT vv[CH];
+        XT xx[CH];
 #pragma unroll
         for (int u = 0; u < CH; u++)
             if (i0 + u < sigma) {
                 cc[u] = ld_stream_i1(c + (i0 + u) * C5_OMEGA, pol_stream);
-                vv[u] = ld_stream_d1(v + (i0 + u) * C5_OMEGA, pol_stream);
+                vv[u] = c5_ld_val(v + (i0 + u) * C5_OMEGA, pol_stream);
             }
 #pragma unroll
         for (int u = 0; u < CH; u++)
@@ -232,57 +250,58 @@ c5_compute_kernel(const int *__restrict__ col, const double *__restrict__ val, c
             if (i < sigma) {
                 if (i > 0 && ((flags >> (31 - i)) & 1u)) {
                     if (direct) {
-                        yt[off ? off[y_offset] : y_offset] = sum;
+                        yt[off ? off[y_offset] : y_offset] = (XT)sum;
                         y_offset++;
                     } else {
                         first_sum = sum;
                     }
                     direct = true;
-                    sum = 0.0;
+                    sum = (AT)0;
                 }
-                sum += vv[u] * xx[u];
+                sum += (AT)vv[u] * (AT)xx[u];
             }
         }
     }
     if (!direct) first_sum = sum;               // no row starts in this lane (lane 0: none after its first entry)
-    double last_sum = sum;
+    AT last_sum = sum;
 
     // ---- partials that belong to a row opened by an earlier lane: segmented sum by warp shuffles.
     // Lane k (k > 0, not starting a row) hands first_sum to the nearest lane j < k that holds a flag.
     const uint32_t present = __ballot_sync(0xffffffffu, flags != 0);
     const bool gives = lane != 0 && !starts_row;
     const int owner = lane ? 31 - __clz(present & ((1u << lane) - 1u)) : -1;     // lane 0 always holds a flag
-    double g = gives ? first_sum : 0.0;
+    AT g = gives ? first_sum : (AT)0;
     const int key = gives ? owner : -2 - lane;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {                                           // suffix sums inside runs of equal key
-        const double gv = __shfl_down_sync(0xffffffffu, g, o);
+        const AT gv = __shfl_down_sync(0xffffffffu, g, o);
         const int gk = __shfl_down_sync(0xffffffffu, key, o);
         if (lane + o < 32 && gk == key) g += gv;
     }
-    const double incoming = __shfl_down_sync(0xffffffffu, g, 1);                 // run of lane j starts at lane j + 1
+    const AT incoming = __shfl_down_sync(0xffffffffu, g, 1);                 // run of lane j starts at lane j + 1
     const int incoming_key = __shfl_down_sync(0xffffffffu, key, 1);
     if (flags != 0 && lane < 31 && incoming_key == lane) last_sum += incoming;
 
-    if (direct) yt[off ? off[y_offset] : y_offset] = last_sum;                    // csr5_spmv_cuda.h:193-195
-    if (lane == 0) carry[t] = direct ? first_sum : last_sum;                      // :198-199
+    if (direct) yt[off ? off[y_offset] : y_offset] = (XT)last_sum;                    // csr5_spmv_cuda.h:193-195
+    if (lane == 0) carry[t] = (double)(direct ? first_sum : last_sum);                      // :198-199
 }
 
 // one thread per tile; the first tile of row R adds R's carries in tile order.  R's entries before that
 // tile were stored by the compute kernel unless R starts exactly on the tile boundary.
+template <typename XT>
 __global__ void c5_calibrate_kernel(const int *__restrict__ row_ptr, const uint32_t *__restrict__ tile_ptr,
-                                    const double *__restrict__ carry, double *__restrict__ y, int p, int T)
+                                    const double *__restrict__ carry, XT *__restrict__ y, int p, int T)
 {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int first_row = (int)(tile_ptr[0] & C5_MASK);
-    for (int r = gid; r < first_row; r += gridDim.x * blockDim.x) y[r] = 0.0;     // leading empty rows
+    for (int r = gid; r < first_row; r += gridDim.x * blockDim.x) y[r] = (XT)0;   // leading empty rows
     const int t = gid;
     if (t >= p) return;
     const uint32_t R = tile_ptr[t] & C5_MASK;
     if (t > 0 && (tile_ptr[t - 1] & C5_MASK) == R) return;
     double sum = 0.0;
     for (int u = t; u < p && (tile_ptr[u] & C5_MASK) == R; u++) sum += carry[u];
-    y[R] = row_ptr[R] == t * T ? sum : y[R] + sum;
+    y[R] = (XT)(row_ptr[R] == t * T ? sum : (double)y[R] + sum);
 }
 
 struct Csr5Format : Format {
@@ -290,9 +309,10 @@ struct Csr5Format : Format {
     DevBuf<int> row_ptr, col, offset_ptr, offset;
     DevBuf<uint32_t> tile_ptr, desc;
     DevBuf<double> val, carry;
-    int tail_rows = 0;
+    DevBuf<float> val32;                  // options.precision = 1 / 2
+    int tail_rows = 0, prec = 0;
 
-    explicit Csr5Format(const b200spmv_options &o) : sigma_opt(o.csr5_sigma) {}
+    explicit Csr5Format(const b200spmv_options &o) : sigma_opt(o.csr5_sigma), prec(o.precision) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -319,7 +339,8 @@ struct Csr5Format : Format {
         B2_TRY(desc.alloc((size_t)p * C5_OMEGA * num_packet));
         B2_TRY(offset_ptr.alloc((size_t)p + 1));
         B2_TRY(col.alloc((size_t)nnz));
-        B2_TRY(val.alloc((size_t)nnz));
+        if (prec) B2_TRY(val32.alloc((size_t)nnz));
+        else B2_TRY(val.alloc((size_t)nnz));
         B2_TRY(carry.alloc((size_t)p));
         B2_CUDA(cudaMemsetAsync(desc.p, 0, desc.bytes() ? desc.bytes() : 4, s));
         DevBuf<int> cnt;
@@ -342,7 +363,8 @@ struct Csr5Format : Format {
             B2_KERNEL_CHECK();
         }
         if (nnz) {
-            c5_transpose_kernel<<<ceil_div(nnz, 256), 256, 0, s>>>(A.col, A.val, tile_ptr.p, nnz, sigma, p, col.p, val.p);
+            if (prec) c5_transpose_kernel<float><<<ceil_div(nnz, 256), 256, 0, s>>>(A.col, A.val, tile_ptr.p, nnz, sigma, p, col.p, val32.p);
+            else c5_transpose_kernel<double><<<ceil_div(nnz, 256), 256, 0, s>>>(A.col, A.val, tile_ptr.p, nnz, sigma, p, col.p, val.p);
             B2_KERNEL_CHECK();
         }
         tail_rows = 0;
@@ -356,21 +378,32 @@ struct Csr5Format : Format {
         return B200SPMV_OK;
     }
 
-    int multiply(const double *x, double *y, cudaStream_t s) override
+    template <typename VT, typename XT, typename AT> int run(const VT *v, const XT *x, XT *y, cudaStream_t s)
     {
         if (nRow == 0) return B200SPMV_OK;
         if (p == 0) {
-            B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
+            B2_CUDA(cudaMemsetAsync(y, 0, sizeof(XT) * (size_t)nRow, s));
             return B200SPMV_OK;
         }
         const int threads = C5_WARPS * 32;
         const int nTileBlocks = ceil_div(p - 1, C5_WARPS), nTailBlocks = ceil_div(tail_rows, threads);
-        c5_compute_kernel<<<nTileBlocks + nTailBlocks, threads, 0, s>>>(col.p, val.p, row_ptr.p, tile_ptr.p, desc.p, offset_ptr.p, offset.p,
-                                                                      x, y, carry.p, nRow, sigma, p, bit_y, bit_y + bit_ss, num_packet,
-                                                                      nTileBlocks);
-        c5_calibrate_kernel<<<ceil_div(p, 256), 256, 0, s>>>(row_ptr.p, tile_ptr.p, carry.p, y, p, C5_OMEGA * sigma);
+        c5_compute_kernel<VT, XT, AT><<<nTileBlocks + nTailBlocks, threads, 0, s>>>(col.p, v, row_ptr.p, tile_ptr.p, desc.p, offset_ptr.p,
+                                                                                  offset.p, x, y, carry.p, nRow, sigma, p, bit_y,
+                                                                                  bit_y + bit_ss, num_packet, nTileBlocks);
+        c5_calibrate_kernel<XT><<<ceil_div(p, 256), 256, 0, s>>>(row_ptr.p, tile_ptr.p, carry.p, y, p, C5_OMEGA * sigma);
         B2_KERNEL_CHECK();
         return B200SPMV_OK;
+    }
+    int multiply(const double *x, double *y, cudaStream_t s) override
+    {
+        if (prec) { set_error("multiply: the handle was created with precision = %d, use b200spmv_multiply_f32", prec); return B200SPMV_ERR_STATE; }
+        return run<double, double, double>(val.p, x, y, s);
+    }
+    int multiply_f32(const float *x, float *y, cudaStream_t s) override
+    {
+        if (!prec) { set_error("multiply_f32: the handle was created with precision = 0 (fp64 vectors)"); return B200SPMV_ERR_STATE; }
+        if (prec == 2) return run<float, float, double>(val32.p, x, y, s);
+        return run<float, float, float>(val32.p, x, y, s);
     }
 
     bool scalar(const std::string &n, long long *out) override
@@ -382,10 +415,12 @@ struct Csr5Format : Format {
         if (n == "num_packet") { *out = num_packet; return true; }
         if (n == "num_offsets") { *out = num_offsets; return true; }
         if (n == "alg_bytes") {   // 12 nnz + 4 (nRow+1) + 4 (p+1) + 4 p omega num_packet + 8 nCol + 8 nRow
-            *out = 12LL * nnz + 4LL * (nRow + 1) + 4LL * (p + 1) + 4LL * p * C5_OMEGA * num_packet + 8LL * nCol + 8LL * nRow;
+            *out = (prec ? 8LL : 12LL) * nnz + 4LL * (nRow + 1) + 4LL * (p + 1) + 4LL * p * C5_OMEGA * num_packet +
+                   (prec ? 4LL : 8LL) * ((long long)nCol + nRow);
             return true;
         }
         if (n == "launches") { *out = p ? 2 : 1; return true; }
+        if (n == "precision") { *out = prec; return true; }
         return false;
     }
 
@@ -397,7 +432,7 @@ struct Csr5Format : Format {
         if (n == "tile_desc_offset_ptr") return export_device(offset_ptr.p, offset_ptr.bytes(), dst, cap);
         if (n == "tile_desc_offset") return export_device(offset.p, offset.bytes(), dst, cap);
         if (n == "col_idx") return export_device(col.p, col.bytes(), dst, cap);
-        if (n == "val") return export_device(val.p, val.bytes(), dst, cap);
+        if (n == "val" && !prec) return export_device(val.p, val.bytes(), dst, cap);
         return -1000;
     }
 };

@@ -23,19 +23,34 @@ def main():
     p0 = int(os.environ.get("MG_CHECK_P0", "512"))
     M = MgSpMat(n_gpu, "crs").convert_synth("lap3d7", p0)
     n, nnz = M.scalar("nRow"), M.scalar("nNnz")
-    x, _ = sp.reference_vectors(n, 0, 3)
-    y = np.full(n, np.nan)
-    M.multiply_host(x, y)
-    torch.cuda.set_device(0)
-    coo = sp.DeviceCoo("lap3d7", p0)
-    A = sp.SpMatOpt("crs").convert_device(coo)
-    coo.free()
-    xd = torch.from_numpy(x).cuda()
-    yd = torch.empty(n, dtype=torch.float64, device="cuda")
-    A.multiply(xd.data_ptr(), yd.data_ptr())
-    torch.cuda.synchronize()
-    same = bool(np.array_equal(y, yd.cpu().numpy()))
-    A.destroy()
+    if os.environ.get("MG_CHECK_NO_SINGLE"):
+        # a matrix one GPU cannot hold (more than 2^31-1 non-zeros in all; every block below that): A.1 = row sums, closed form
+        x = np.ones(n)
+        y = np.full(n, np.nan)
+        M.multiply_host(x, y)
+        r = np.arange(n, dtype=np.int64)
+
+        def span(i):
+            return 1 + (i > 0).astype(np.int64) + (i < p0 - 1).astype(np.int64)
+        cnt = span(r // (p0 * p0)) + span((r // p0) % p0) + span(r % p0) - 2
+        same = bool(np.array_equal(y, (7 - cnt).astype(np.float64)))
+        assert nnz == int(cnt.sum())
+        del r, cnt
+    else:
+        x, _ = sp.reference_vectors(n, 0, 3)
+        y = np.full(n, np.nan)
+        M.multiply_host(x, y)
+        torch.cuda.set_device(0)
+        coo = sp.DeviceCoo("lap3d7", p0)
+        A = sp.SpMatOpt("crs").convert_device(coo)
+        coo.free()
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.empty(n, dtype=torch.float64, device="cuda")
+        A.multiply(xd.data_ptr(), yd.data_ptr())
+        torch.cuda.synchronize()
+        same = bool(np.array_equal(y, yd.cpu().numpy()))
+        A.destroy()
+        del xd, yd
     M.upload_x(x)
     for _ in range(5):
         M.multiply()
