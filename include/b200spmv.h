@@ -181,6 +181,10 @@ typedef struct {
 B200SPMV_API int b200spmv_synth(int kind, long long p0, long long p1, unsigned long long seed,
                    int rowBegin, int rowEnd, b200spmv_coo *out, void *stream);
 B200SPMV_API int b200spmv_coo_free(b200spmv_coo *coo);
+/* Uploads entries of rows [rowBegin,rowEnd) of a sorted host COO (row ids stay global): the block a rank of the
+ * row-partitioned multiply owns when the matrix comes from a file instead of a generator. */
+B200SPMV_API int b200spmv_coo_upload(int nRow, int nCol, int rowBegin, int rowEnd, long long nnz, const int *row_h,
+                        const int *col_h, const double *val_h, b200spmv_coo *out);
 /* Copies the triplets to host arrays of coo->nnz entries (parity checks, CPU baseline input). */
 B200SPMV_API int b200spmv_coo_download(const b200spmv_coo *coo, int *row_h, int *col_h, double *val_h);
 

@@ -65,6 +65,7 @@ def _load():
     lib.b200spmv_get_array.restype = ll
     lib.b200spmv_synth.argtypes = [ip, ll, ll, C.c_ulonglong, ip, ip, C.POINTER(Coo), vp]
     lib.b200spmv_coo_free.argtypes = [C.POINTER(Coo)]
+    lib.b200spmv_coo_upload.argtypes = [ip, ip, ip, ip, ll, vp, vp, vp, C.POINTER(Coo)]
     lib.b200spmv_coo_download.argtypes = [C.POINTER(Coo), vp, vp, vp]
     lib.b200spmv_reference_vectors.argtypes = [C.c_uint, ip, ip, vp, vp]
     lib.b200spmv_load_mtx.argtypes = [C.c_char_p, ip, C.POINTER(Coo), vp]

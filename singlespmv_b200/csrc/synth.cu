@@ -254,6 +254,26 @@ extern "C" int b200spmv_synth(int kind, long long p0, long long p1, unsigned lon
     return B200SPMV_OK;
 }
 
+// rows [rowBegin, rowEnd) of a host COO (global row ids, sorted) -> device arrays owned by *out
+extern "C" int b200spmv_coo_upload(int nRow, int nCol, int rowBegin, int rowEnd, long long nnz, const int *row_h,
+                                   const int *col_h, const double *val_h, b200spmv_coo *out)
+{
+    clear_error();
+    if (!out || nnz < 0 || (nnz > 0 && (!row_h || !col_h || !val_h)) || rowBegin < 0 || rowEnd < rowBegin || rowEnd > nRow) {
+        set_error("coo_upload: bad argument");
+        return B200SPMV_ERR_INVALID;
+    }
+    memset(out, 0, sizeof *out);
+    out->nRow = nRow; out->nCol = nCol; out->rowBegin = rowBegin; out->rowEnd = rowEnd;
+    B2_TRY(alloc_coo(out, nnz));
+    if (nnz) {
+        B2_CUDA(cudaMemcpy(out->row_d, row_h, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+        B2_CUDA(cudaMemcpy(out->col_d, col_h, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice));
+        B2_CUDA(cudaMemcpy(out->val_d, val_h, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return B200SPMV_OK;
+}
+
 extern "C" int b200spmv_coo_free(b200spmv_coo *coo)
 {
     if (!coo) return B200SPMV_OK;

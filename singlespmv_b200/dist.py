@@ -48,17 +48,35 @@ def plan_requests(halo_cols, bounds, rank, all_to_all_counts, all_to_all_lists):
     return need, asked, send_cols
 
 
+def host_bounds(row_idx, nRow, nParts):
+    """Row split of a sorted host COO where the running non-zero count passes g nnz / nParts -- the rule of
+    b200spmv_partition_rows (csrc/halo.cu) and b200spmv_mg_convert_coo_host, on the host."""
+    nnz = len(row_idx)
+    b = np.zeros(nParts + 1, np.int64)
+    b[nParts] = nRow
+    for g in range(1, nParts):
+        e = nnz * g // nParts
+        if e >= nnz:
+            bnd = nRow
+        else:
+            r = int(row_idx[e])
+            bnd = r if (e == 0 or int(row_idx[e - 1]) != r) else r + 1
+        b[g] = max(bnd, b[g - 1])
+    return b
+
+
 class Block:
-    """One rank's share: local matrix (any format, default CRS), halo bookkeeping, device buffers."""
+    """One rank's share: local matrix (any format, default CRS), halo bookkeeping, device buffers.
+    kind = a synthetic generator name, or a plugin.SpMat (host COO: the rank uploads only its own rows)."""
 
     def __init__(self, kind, p0, p1, seed, bounds, rank, fmt="crs", stream=None, crs_path=None):
         import os
         import torch
         self.rank, self.bounds = rank, [int(b) for b in bounds]
         rb, re = self.bounds[rank], self.bounds[rank + 1]
-        coo = DeviceCoo(kind, p0, p1, seed, rb, re) if re > rb else None
-        if coo is None:
+        if re <= rb:
             raise ValueError("rank %d owns no rows" % rank)
+        coo = DeviceCoo(kind, p0, p1, seed, rb, re) if isinstance(kind, str) else DeviceCoo.from_host_rows(kind, rb, re)
         self.global_nnz_local = coo.nNnz
         self.halo = C.c_void_p()
         check(lib.b200spmv_halo_plan(C.byref(coo.c), rb, re, C.byref(self.halo), stream))
@@ -199,7 +217,8 @@ class DistSpmv:
         import torch.distributed as dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.bounds = synth_bounds(kind, p0, p1, self.world)
+        # kind: generator name (every rank generates its own rows in HBM) or a plugin.SpMat every rank holds on the host
+        self.bounds = synth_bounds(kind, p0, p1, self.world) if isinstance(kind, str) else host_bounds(kind.row_idx, kind.nRow, self.world)
         self.block = Block(kind, p0, p1, seed, self.bounds, self.rank, fmt)
         need, asked, send_cols = _dist_plan(self.block, self.world, self.device)
         self.block.set_requests(need, asked, send_cols)

@@ -61,6 +61,16 @@ class DeviceCoo:
         self._dims()
         return self
 
+    @classmethod
+    def from_host_rows(cls, A, row_begin, row_end):
+        """Rows [row_begin, row_end) of a host SpMat (sorted COO) as a device COO with global row ids."""
+        self = cls(None, 0)
+        e0, e1 = np.searchsorted(A.row_idx, [row_begin, row_end], side="left")
+        check(lib.b200spmv_coo_upload(A.nRow, A.nCol, int(row_begin), int(row_end), int(e1 - e0), _ptr(A.row_idx[e0:e1]),
+                                      _ptr(A.col_idx[e0:e1]), _ptr(A.val[e0:e1]), C.byref(self.c)))
+        self._dims()
+        return self
+
     def to_host(self):
         n = self.nNnz
         row, col, val = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)

@@ -113,6 +113,11 @@ void SpMV (const SpMatOpt &A, const VecOpt &x, Vec &y) {
         (void)x; (void)y;
         b200_check(b200spmv_mg_multiply(A.mg), "mg_multiply");
 #else
+        static const double *registered_y_mg = NULL;          // page-lock the driver's y once: asynchronous D2H from every GPU
+        if (registered_y_mg != y.val && y.size > 0 && !getenv("B200_NO_HOST_REGISTER")) {
+            b200spmv_host_register(y.val, sizeof(double) * (unsigned long long)y.size);
+            registered_y_mg = y.val;
+        }
         b200_check(b200spmv_mg_multiply_host(A.mg, x.val, y.val), "mg_multiply_host");
 #endif
         return;

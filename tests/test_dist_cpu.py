@@ -79,3 +79,23 @@ def test_owner_counts():
     from singlespmv_b200.dist import owner_counts
     assert owner_counts([0, 1, 5, 9, 10], [0, 4, 8, 12]).tolist() == [2, 1, 2]
     assert owner_counts([], [0, 4, 8]).tolist() == [0, 0]
+
+
+def test_host_bounds_rule():
+    """host_bounds = the split rule of b200spmv_partition_rows / b200spmv_mg_convert_coo_host on a host COO: block g starts at
+    the row holding entry g nnz / G (the next row when that entry is not the row's first); monotone, covers all rows."""
+    from singlespmv_b200.dist import host_bounds
+    rng = np.random.default_rng(1)
+    for nRow, parts in ((10, 3), (1000, 8), (7, 7), (50, 2)):
+        lens = rng.integers(0, 9, nRow)
+        lens[rng.integers(0, nRow)] = 300                       # one heavy row
+        row = np.repeat(np.arange(nRow), lens).astype(np.int32)
+        b = host_bounds(row, nRow, parts)
+        assert b[0] == 0 and b[-1] == nRow and np.all(np.diff(b) >= 0)
+        ptr = np.concatenate([[0], np.cumsum(lens)])
+        for g in range(1, parts):
+            e = len(row) * g // parts
+            assert ptr[b[g]] >= e or b[g] == nRow             # the block starts at or after the balance point ...
+            if b[g] > 0 and b[g] > b[g - 1]:
+                assert ptr[b[g] - 1] <= e                     # ... and no earlier row boundary would have done
+    assert list(host_bounds(np.zeros(0, np.int32), 4, 2)) == [0, 4, 4]
