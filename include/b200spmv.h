@@ -242,6 +242,31 @@ B200SPMV_API int b200spmv_halo_set_send(b200spmv_halo *h, const int *send_cols_h
 B200SPMV_API int b200spmv_halo_pack(const b200spmv_halo *h, const double *x_owned_d, double *sendbuf_d, void *stream);
 B200SPMV_API int b200spmv_halo_free(b200spmv_halo *h);
 
+/* ---- x windows: the halo exchange of the one-process-per-GPU path as ONE kernel over NVLink peer memory
+ * (csrc/xwin.cu; host side singlespmv_b200/dist.py).  Every rank keeps x_ext = [left halo | owned | right halo] in a
+ * cudaMalloc'ed window that the other processes of the node map through CUDA IPC; per step one kernel signals "my
+ * slice is in place" into the readers' windows, waits for the owners' signals, pulls exactly its halo entries out of the
+ * owners' slices and acknowledges -- no pack kernel, no staging buffer, no NCCL kernels.  When the step's kernel has
+ * finished, every reader has finished pulling: the owned slice may be overwritten. */
+typedef struct b200spmv_xwin b200spmv_xwin;
+/* nExt doubles of x_ext on the current device, the owned slice starts at ownedOff (= nLeft) */
+B200SPMV_API int b200spmv_xwin_create(int rank, int world, long long nExt, long long ownedOff, b200spmv_xwin **out);
+B200SPMV_API void *b200spmv_xwin_x_ext(b200spmv_xwin *w);               /* device pointer of x_ext */
+/* 80-byte blob (cudaIpcMemHandle_t + layout) to hand to the other ranks, and its counterpart */
+B200SPMV_API int b200spmv_xwin_export(b200spmv_xwin *w, void *blob80);
+B200SPMV_API int b200spmv_xwin_import(b200spmv_xwin *w, int peer, const void *blob80);
+/* same-process twin of export + import (several blocks driven by one process) */
+B200SPMV_API int b200spmv_xwin_attach(b200spmv_xwin *w, int peer, b200spmv_xwin *other);
+/* halo_cols_h: b200spmv_halo_cols (global ids, ascending); bounds_h[world+1]: the column split; readers_h: ranks that
+ * asked this one for columns */
+B200SPMV_API int b200spmv_xwin_plan(b200spmv_xwin *w, const int *halo_cols_h, int nHalo, int nLeft, int nLocal,
+                       const long long *bounds_h, const int *readers_h, int nReaders);
+/* one step's exchange, asynchronous on `stream` (may be captured in a CUDA graph); every rank calls it once per step */
+B200SPMV_API int b200spmv_xwin_exchange(b200spmv_xwin *w, void *stream);
+/* steps finished; *timed_out != 0 if a flag wait ever gave up after ~2 s (a peer that did not take part) */
+B200SPMV_API int b200spmv_xwin_status(b200spmv_xwin *w, long long *steps, int *timed_out);
+B200SPMV_API int b200spmv_xwin_free(b200spmv_xwin *w);
+
 /* ---- Matrix-Market ingest into a device COO.  The reference's loader (src/util.cpp:30-66)
  * ignores the banner and keeps duplicates; the CSR5 benchmark it vendors reads the same files through mmio and
  * honours symmetric / pattern banners (opt/Benchmark_SpMV_using_CSR5/CSR5_avx2/main.cpp:145-282). */

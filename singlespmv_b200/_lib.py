@@ -91,6 +91,16 @@ def _load():
     lib.b200spmv_halo_set_send.argtypes = [vp, vp, ll]
     lib.b200spmv_halo_pack.argtypes = [vp, vp, vp, vp]
     lib.b200spmv_halo_free.argtypes = [vp]
+    lib.b200spmv_xwin_create.argtypes = [ip, ip, ll, ll, C.POINTER(vp)]
+    lib.b200spmv_xwin_x_ext.argtypes = [vp]
+    lib.b200spmv_xwin_x_ext.restype = vp
+    lib.b200spmv_xwin_export.argtypes = [vp, vp]
+    lib.b200spmv_xwin_import.argtypes = [vp, ip, vp]
+    lib.b200spmv_xwin_attach.argtypes = [vp, ip, vp]
+    lib.b200spmv_xwin_plan.argtypes = [vp, vp, ip, ip, ip, vp, vp, ip]
+    lib.b200spmv_xwin_exchange.argtypes = [vp, vp]
+    lib.b200spmv_xwin_status.argtypes = [vp, C.POINTER(ll), C.POINTER(ip)]
+    lib.b200spmv_xwin_free.argtypes = [vp]
     return lib
 
 

@@ -7,12 +7,15 @@ balance with the x halo exchange overlapped with the local block.  Layering:
 * device work (partition by nnz, halo discovery, column renumbering, pack kernel, multiply of a row range)
   is behind the C-ABI: b200spmv_partition_*, b200spmv_halo_*, b200spmv_multiply_rows;
 * this file is host plumbing only: who asks whom for which x entries (``plan_requests``), and per multiply
-  the grouped NCCL send/recv on a communication stream while the interior rows run on the compute stream.
+  the exchange on a communication stream while the interior rows run on the compute stream.
 
 Per multiply on every rank:
-    comm stream   : pack owned x entries the peers need -> grouped isend/irecv straight into x_ext's halo slots
+    comm stream   : the exchange.  Default ("peer"): ONE kernel over NVLink peer memory (csrc/xwin.cu) -- x_ext lives in
+                    a window the other ranks map through CUDA IPC; the kernel signals, waits for the owners, pulls its
+                    halo entries out of their slices and acknowledges.  Fallback ("nccl", B200SPMV_DIST_EXCHANGE=nccl or
+                    when the windows cannot be mapped): pack kernel + grouped isend/irecv into x_ext's halo slots.
     compute stream: rows that touch no halo column            (b200spmv_multiply_rows, > 99 % of config 5)
-    compute stream: after the receives land, the boundary rows at both ends of the block
+    compute stream: after the halo has landed, the boundary rows at both ends of the block
 """
 import ctypes as C
 
@@ -65,6 +68,27 @@ def host_bounds(row_idx, nRow, nParts):
     return b
 
 
+class _DevArray:
+    """A device pointer with the CUDA array interface, so that torch can view library-owned memory without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_array(ptr, n, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, n), device=device)
+
+
+def plan_window(win, block, bounds, send_counts):
+    """Pull plan of an x window: owners of the halo columns, and the ranks that read this one's slice."""
+    readers = np.ascontiguousarray([p for p, c in enumerate(send_counts) if c], np.int32)
+    b64 = np.ascontiguousarray(bounds, np.int64)
+    hc = np.ascontiguousarray(block.halo_cols, np.int32)
+    check(lib.b200spmv_xwin_plan(win, _ptr(hc) if len(hc) else None, len(hc), block.nLeft, block.nLocal, _ptr(b64),
+                                 _ptr(readers) if len(readers) else None, len(readers)))
+
+
 class Block:
     """One rank's share: local matrix (any format, default CRS), halo bookkeeping, device buffers.
     kind = a synthetic generator name, or a plugin.SpMat (host COO: the rank uploads only its own rows)."""
@@ -104,10 +128,20 @@ class Block:
         self.y = torch.full((self.nRows,), float("nan"), dtype=torch.float64, device="cuda")
         self.sendbuf = None
         self.recv_counts = self.send_counts = None
+        self.win = None
 
     @property
     def x_owned(self):
         return self.x_ext[self.nLeft:self.nLeft + self.nLocal]
+
+    def use_window(self, win):
+        """x_ext moves into an x window (csrc/xwin.cu) that the peers can map; call before set_requests."""
+        import torch
+        n = self.nLeft + self.nLocal + self.nRight
+        self.win = win
+        self.x_ext = device_array(lib.b200spmv_xwin_x_ext(win), n, self.x_ext.device) if n else self.x_ext
+        self.x_ext.zero_()
+        torch.cuda.synchronize()
 
     def set_requests(self, recv_counts, send_counts, send_cols):
         import torch
@@ -148,6 +182,10 @@ class Block:
         return per * parts + (1 if self.sendbuf is not None and sum(self.send_counts) else 0)
 
     def free(self):
+        if self.win:
+            self.x_ext = None
+            lib.b200spmv_xwin_free(self.win)
+            self.win = None
         if self.halo:
             lib.b200spmv_halo_free(self.halo)
             self.halo = C.c_void_p()
@@ -161,12 +199,25 @@ def synth_bounds(kind, p0, p1, nParts):
 
 
 # ------------------------------------------------------------------------------------------ all ranks in one process (tests)
-def build_local_group(kind, p0, p1, seed, nParts, fmt="crs"):
+def build_local_group(kind, p0, p1, seed, nParts, fmt="crs", windows=False):
     """All blocks on ONE GPU in one process: the same device code and the same request planning as the
-    NCCL path, with device-to-device copies standing in for send/recv (parity tests on a 1-GPU box)."""
+    torchrun path (parity tests on a 1-GPU box).  windows=False: device-to-device copies stand in for NCCL send/recv;
+    windows=True: every block's x_ext sits in an x window attached to the others (local_group_exchange_windows)."""
     bounds = synth_bounds(kind, p0, p1, nParts)
     blocks = [Block(kind, p0, p1, seed, bounds, r, fmt) for r in range(nParts)]
     need = [owner_counts(b.halo_cols, bounds) for b in blocks]
+    if windows:
+        wins = []
+        for r, b in enumerate(blocks):
+            w = C.c_void_p()
+            check(lib.b200spmv_xwin_create(r, nParts, b.nLeft + b.nLocal + b.nRight, b.nLeft, C.byref(w)))
+            wins.append(w)
+        for r, b in enumerate(blocks):
+            for p in range(nParts):
+                if p != r:
+                    check(lib.b200spmv_xwin_attach(wins[r], p, wins[p]))
+            plan_window(wins[r], b, bounds, [need[p][r] for p in range(nParts)])
+            b.use_window(wins[r])
     for r, b in enumerate(blocks):
         asked = np.array([need[p][r] for p in range(nParts)], np.int64)
         lists = []
@@ -186,6 +237,21 @@ def local_group_multiply(blocks):
         for p, view in b.recv_views.items():
             view.copy_(blocks[p].send_views[b.rank])
     for b in blocks:
+        b.multiply_boundary()
+
+
+def local_group_multiply_windows(blocks, streams):
+    """The torchrun step with all ranks in one process: every block's exchange kernel on its own stream (they wait for
+    each other's flags, so they must be able to run at the same time), then the multiplies."""
+    import torch
+    cur = torch.cuda.current_stream()
+    for b, st in zip(blocks, streams):
+        st.wait_stream(cur)
+        check(lib.b200spmv_xwin_exchange(b.win, C.c_void_p(st.cuda_stream)))
+    for b in blocks:
+        b.multiply_interior()
+    for b, st in zip(blocks, streams):
+        cur.wait_stream(st)
         b.multiply_boundary()
 
 
@@ -212,7 +278,7 @@ def _dist_plan(block, world, device):
 class DistSpmv:
     """The per-rank engine used by bench.py --gpus N (and usable as a library)."""
 
-    def __init__(self, kind, p0, p1, seed, fmt="crs"):
+    def __init__(self, kind, p0, p1, seed, fmt="crs", exchange=None):
         import torch
         import torch.distributed as dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -221,6 +287,11 @@ class DistSpmv:
         self.bounds = synth_bounds(kind, p0, p1, self.world) if isinstance(kind, str) else host_bounds(kind.row_idx, kind.nRow, self.world)
         self.block = Block(kind, p0, p1, seed, self.bounds, self.rank, fmt)
         need, asked, send_cols = _dist_plan(self.block, self.world, self.device)
+        import os
+        self.exchange = exchange or os.environ.get("B200SPMV_DIST_EXCHANGE", "peer")
+        self.exchange_error = None
+        if self.exchange == "peer" and not self._map_windows(asked):
+            self.exchange = "nccl"
         self.block.set_requests(need, asked, send_cols)
         self.compute = torch.cuda.current_stream()
         # highest priority: the tiny pack kernel (and NCCL's own kernels, TORCH_NCCL_HIGH_PRIORITY below) must not queue
@@ -229,22 +300,63 @@ class DistSpmv:
         self.comm = torch.cuda.Stream(priority=-1)
         self.graph, self.graph_error = None, None
 
-    def _step_eager(self):
-        """pack + grouped NCCL send/recv on the comm stream, interior rows on the current stream meanwhile,
-        boundary rows once the receives have landed."""
+    def _map_windows(self, send_counts):
+        """x_ext into an x window, every peer's window mapped through CUDA IPC.  All ranks succeed or all fall back."""
         import torch
         import torch.distributed as dist
         b = self.block
-        cur = torch.cuda.current_stream()
-        cptr = C.c_void_p(cur.cuda_stream)
-        self.comm.wait_stream(cur)                           # previous readers of x_ext / writers of x_owned are ordered before
+        ok, win = 1, C.c_void_p()
+        blob = np.zeros(80, np.uint8)
+        try:
+            check(lib.b200spmv_xwin_create(self.rank, self.world, b.nLeft + b.nLocal + b.nRight, b.nLeft, C.byref(win)))
+            check(lib.b200spmv_xwin_export(win, _ptr(blob)))
+        except Exception as e:                               # noqa: BLE001
+            ok, self.exchange_error = 0, repr(e)
+        mine = torch.from_numpy(blob).to(self.device)
+        blobs = torch.empty(self.world * 80, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(blobs, mine)
+        blobs = blobs.cpu().numpy().reshape(self.world, 80)
+        if ok:
+            try:
+                for p in range(self.world):
+                    if p != self.rank:
+                        check(lib.b200spmv_xwin_import(win, p, _ptr(np.ascontiguousarray(blobs[p]))))
+                plan_window(win, b, self.bounds, send_counts)
+            except Exception as e:                           # noqa: BLE001
+                ok, self.exchange_error = 0, repr(e)
+        t = torch.tensor([ok], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if not int(t.item()):
+            if win:
+                lib.b200spmv_xwin_free(win)
+            return False
+        b.use_window(win)
+        return True
+
+    def _exchange(self):
+        """The halo exchange on the comm stream (which the caller has already ordered after the writers of x_owned)."""
+        import torch
+        import torch.distributed as dist
+        b = self.block
+        if self.exchange == "peer":
+            check(lib.b200spmv_xwin_exchange(b.win, C.c_void_p(self.comm.cuda_stream)))
+            return
         with torch.cuda.stream(self.comm):
             b.pack(C.c_void_p(self.comm.cuda_stream))
             ops = [dist.P2POp(dist.irecv, v, p) for p, v in b.recv_views.items()]
             ops += [dist.P2POp(dist.isend, v, p) for p, v in b.send_views.items()]
-            works = dist.batch_isend_irecv(ops) if ops else []
-            for w in works:
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
                 w.wait()                                     # comm stream waits for NCCL's stream
+
+    def _step_eager(self):
+        """the exchange on the comm stream, interior rows on the current stream meanwhile, boundary rows once the halo
+        has landed."""
+        import torch
+        b = self.block
+        cur = torch.cuda.current_stream()
+        cptr = C.c_void_p(cur.cuda_stream)
+        self.comm.wait_stream(cur)                           # previous readers of x_ext / writers of x_owned are ordered before
+        self._exchange()
         b.multiply_interior(cptr)                            # overlaps the exchange
         cur.wait_stream(self.comm)
         b.multiply_boundary(cptr)
@@ -276,7 +388,6 @@ class DistSpmv:
         """One multiply with host vectors: H2D of the owned x slice (pieces), exchange + multiply, D2H of the owned
         y slice (chunks) -- all three overlapped; returns without synchronising (streams h_out / current hold the tail)."""
         import torch
-        import torch.distributed as dist
         b = self.block
         cur = torch.cuda.current_stream()
         cptr = C.c_void_p(cur.cuda_stream)
@@ -290,13 +401,8 @@ class DistSpmv:
                     b.x_owned[p0:p1].copy_(x_pin[p0:p1], non_blocking=True)
                 self.h_ev_in[k].record(self.h_in)
         self.comm.wait_stream(cur)
-        self.comm.wait_event(self.h_ev_in[-1])                   # the send lists touch both ends of the slice
-        with torch.cuda.stream(self.comm):
-            b.pack(C.c_void_p(self.comm.cuda_stream))
-            ops = [dist.P2POp(dist.irecv, v, p) for p, v in b.recv_views.items()]
-            ops += [dist.P2POp(dist.isend, v, p) for p, v in b.send_views.items()]
-            for w in (dist.batch_isend_irecv(ops) if ops else []):
-                w.wait()
+        self.comm.wait_event(self.h_ev_in[-1])                   # the peers read both ends of the slice
+        self._exchange()
         for i, (rb, re) in enumerate(self.h_chunks):
             if self.h_need[i] >= 0:
                 cur.wait_event(self.h_ev_in[self.h_need[i]])
@@ -353,6 +459,26 @@ class DistSpmv:
             self._step_eager()
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this process (and allocate its page-locked vectors, first touch) on the CPUs NVML reports as closest to the
+    GPU: 8 ranks staging 2 x 1 GB per step through one socket's memory was the e2e limit (15 ms at 2 and at 8 GPUs).
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is not available."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:                                        # noqa: BLE001
+        return None
+
+
 def run_partitioned_bench(args, wl, wl_key):
     """bench.py --gpus N (N > 1): strong scaling of one matrix over N ranks, launched by torchrun."""
     import json
@@ -380,6 +506,7 @@ def run_partitioned_bench(args, wl, wl_key):
     from .plugin import reference_vectors
     x_h, _ = reference_vectors(nRow, 0, 3)
     lo, hi = int(eng.bounds[rank]), int(eng.bounds[rank + 1])
+    numa = bind_to_gpu_numa_node(local_rank)                   # page-locked vectors on the memory next to this GPU's PCIe root
     x_pin = torch.from_numpy(x_h[lo:hi].copy()).pin_memory()
     y_pin = torch.empty(b.nRows, dtype=torch.float64).pin_memory()
     del x_h
@@ -489,11 +616,14 @@ def run_partitioned_bench(args, wl, wl_key):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl_key + ": " + wl["name"], "format": fmt, "nRow": nRow, "nCol": nRow, "nnz": nnz,
-                           "parallelism": "row blocks by nnz balance x%d, x halo %d doubles/step over NCCL send/recv "
-                                          "overlapped with interior rows" % (world, halo_total),
+                           "parallelism": "row blocks by nnz balance x%d, x halo %d doubles/step %s, overlapped with interior rows"
+                                          % (world, halo_total, "pulled out of the owners' x windows over NVLink peer memory "
+                                             "(CUDA IPC) by one exchange kernel per rank" if eng.exchange == "peer" else
+                                             "over NCCL send/recv"),
+                           "exchange": eng.exchange, "exchange_fallback_reason": eng.exchange_error,
                            "local_kernel": ("crs_tma_kernel (row-chunk stream)" if fmt == "crs" and b.A.scalar("short_row_path") else
                                             "tile_stream_kernel" if fmt in ("crs", "ss", "css") else fmt),
-                           "launch": "one CUDA graph per step (both streams + NCCL captured)" if graphed else "eager launches",
+                           "launch": "one CUDA graph per step (both streams captured)" if graphed else "eager launches",
                            "eager_ms_per_step": eager_full_ms, "compute_only_ms_per_step": compute_only_ms,
                            "exposed_exchange_ms": max(0.0, eager_full_ms - compute_only_ms),
                            "l2": "inputs larger than L2 (%.2f GB per GPU per step)" % (alg_bytes / world / 1e9)},
@@ -502,7 +632,7 @@ def run_partitioned_bench(args, wl, wl_key):
                              "peak_source": peak_src + " x %d GPUs" % world, "alg_bytes_per_launch": alg_bytes,
                              "kernel": "CRS multiply (crs_tma_kernel for short rows, else tile_stream_kernel): whole step incl. exposed halo exchange"},
                 "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
-                        "h2d_bytes_per_step": 8 * nRow, "d2h_bytes_per_step": 8 * nRow},
+                        "h2d_bytes_per_step": 8 * nRow, "d2h_bytes_per_step": 8 * nRow, "host_cpus_bound": numa},
                 "gpu_launches": int(launches.item()) * args.steps, "clocks": clocks}
         if parity is not None:
             line["parity"] = parity

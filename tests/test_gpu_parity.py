@@ -579,6 +579,40 @@ def test_partitioned_blocks_match_single_gpu(sp, oracle, kind, n, parts):
         b.free()
 
 
+@pytest.mark.parametrize("kind,n,parts", [("lap3d7", 24, 2), ("lap3d7", 24, 5), ("box3d27", 14, 3), ("uniform", 4096, 4)])
+def test_x_window_exchange_kernel(sp, oracle, kind, n, parts):
+    """The peer-memory exchange of the torchrun path (csrc/xwin.cu) with every rank's window in one process on one GPU:
+    flags, pull and acknowledgement over several steps with a NEW x each step; y bit-identical to the reference CRS."""
+    import ctypes as C
+    import torch
+    from singlespmv_b200 import dist as spd
+    from singlespmv_b200._lib import lib
+    if kind == "uniform":
+        nr, nc, row, col, val = oracle.uniform(1, n, n, 8)
+        p1 = 8
+    else:
+        nr, nc, row, col, val = oracle.stencil(kind, n)
+        p1 = 0
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    bounds, blocks = spd.build_local_group(kind, n, p1, 1, parts, windows=True)
+    streams = [torch.cuda.Stream() for _ in blocks]
+    xd = torch.from_numpy(x).cuda()
+    for step, scale in enumerate((1.0, 2.0, 0.5, 1.0)):
+        for b in blocks:
+            lo, hi = int(bounds[b.rank]), int(bounds[b.rank + 1])
+            b.x_owned.copy_(xd[lo:hi] * scale)
+        spd.local_group_multiply_windows(blocks, streams)
+        torch.cuda.synchronize()
+        y = torch.cat([b.y for b in blocks]).cpu().numpy()
+        assert np.array_equal(y, y_ref * scale), "step %d" % step
+    for b in blocks:
+        steps, bad = C.c_longlong(), C.c_int()
+        assert lib.b200spmv_xwin_status(b.win, C.byref(steps), C.byref(bad)) == 0
+        assert steps.value == 4 and bad.value == 0
+        b.free()
+
+
 def test_partition_rows_from_coo(sp, oracle):
     import ctypes as C
     from singlespmv_b200._lib import lib, check
