@@ -61,7 +61,7 @@ HEADLINE = "c5"
 # ncu --set full captures (profiles/r1_ncu_kernels.md, profiles/r2_ncu_kernels.md).  Keyed by (workload, format); else null.
 NCU_TRAFFIC = {("c2", "css"): 3 * 2415011680, ("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
                ("c4", "dia"): 3870562096, ("c4", "ell"): 5853024560, ("c5", "dia"): 9634725000,
-               ("c5", "csr5"): 13638726000, ("c5", "coo"): 20025184000}
+               ("c5", "csr5"): 13638726000}
 try:                                    # captures of this round's kernels, written by scripts/ncu_traffic.py
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
         for _k, _v in json.load(_f).items():
@@ -70,7 +70,7 @@ except Exception:
     pass
 DOMINANT = {"crs": "crs_tma_kernel (longest row <= 16) / tile_stream_kernel", "ss": "crs_tma_kernel / tile_stream_kernel",
             "css": "tile_stream_kernel (one launch per column block)", "ell": "ell_spmv_kernel / cbs_spmv_kernel (column-blocked)",
-            "jds": "jds_spmv_kernel / cbs_spmv_kernel (column-blocked)", "dia": "dia_spmv_tma_kernel", "coo": "coo_tile_kernel",
+            "jds": "jds_spmv_kernel / cbs_spmv_kernel (column-blocked)", "dia": "dia_spmv_tma_kernel", "coo": "coo_stream_kernel",
             "csr5": "c5_compute_kernel", "hyb": "ell_spmv_kernel + coo_tile_kernel"}
 
 

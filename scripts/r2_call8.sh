@@ -1,0 +1,30 @@
+# Round 2, GPU call 8 (1 GPU): COO entry stream (parity + bench variants), x-window exchange kernel in one process.
+mkdir -p gpurun_out
+TAG=r2c8
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coo or x_window or hyb or full_size_stencils" > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
+tail -6 gpurun_out/pytest_$TAG.log
+b() { # tag, env..., -- bench args
+  tag=$1; shift
+  env "$@" timeout 300 python bench.py --no-cpu --steps 20 --warmup 5 $BARGS > gpurun_out/bench_${TAG}_$tag.json 2> gpurun_out/bench_${TAG}_$tag.err
+  python - gpurun_out/bench_${TAG}_$tag.json $tag <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print(sys.argv[2], "GF %.1f ms %.4f frac %.3f" % (d["value"], d["ms_per_step"], d["roofline"]["frac"]))
+except Exception as e:
+    print(sys.argv[2], "no result", e)
+PY
+}
+BARGS="--workload c5 --format coo"
+b c5_coo_e2048 X=1
+b c5_coo_e1024 B200SPMV_COO_E=1024
+b c5_coo_e2048_c2 B200SPMV_COO_CTAS=2
+b c5_coo_e1024_c4 B200SPMV_COO_E=1024 B200SPMV_COO_CTAS=4
+b c5_coo_tile B200SPMV_COO_PATH=tile
+BARGS="--workload c3 --format coo"
+b c3_coo X=1
+b c3_coo_tile B200SPMV_COO_PATH=tile
+BARGS="--workload c4 --format coo"
+b c4_coo X=1
+BARGS="--workload c1 --format coo"
+b c1_coo X=1

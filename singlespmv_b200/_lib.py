@@ -21,7 +21,7 @@ class B200SpmvError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("segment_width", C.c_int), ("n_block", C.c_int), ("csr5_sigma", C.c_int),
-                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("precision", C.c_int), ("hyb_k", C.c_int), ("reserved", C.c_int * 6)]
+                ("ss_faithful", C.c_int), ("value_f32", C.c_int), ("crs_path", C.c_int), ("profile", C.c_int), ("col_blocks", C.c_int), ("precision", C.c_int), ("hyb_k", C.c_int), ("coo_path", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class Stats(C.Structure):

@@ -10,6 +10,10 @@
 // The thread that finds a run start also zero-fills the empty rows in front of it (beta = 0).  Runs
 // crossing a tile boundary are finished by a second tiny kernel (short: recomputed sequentially;
 // long: per-tile carries added in tile order -> deterministic).
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -167,23 +171,191 @@ __global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The entry stream ("coo_stream"): the default COO multiply.  BASELINE.json asks for "COO ... tile segmented reductions
+// using warp shuffles"; the tile kernel above parks every product in shared memory and reads it back (MIO-bound, 0.51
+// of the roofline on c5).  Here:
+//   * persistent CTAs; the 16 B/entry stream (row, col, val) of tile k+1 is brought into shared memory by three 1-D TMA
+//     bulk copies while tile k is reduced -- no thread ever waits for matrix data;
+//   * a warp owns CS_CHUNK consecutive entries of the tile, 128 at a time: a lane multiplies 4 consecutive entries,
+//     reduces the runs of equal row ids that start AND end inside them in registers, and one segmented warp scan
+//     (5 shuffle steps) finishes the runs that cross lanes; the open run is carried in a register to the next 128;
+//   * a chunk writes y for every run that STARTS in it (and zero-fills the empty rows in front of each run: beta = 0);
+//     the leading entries that continue a run of an earlier chunk go to carry[chunk], and the fix-up kernel adds the
+//     carries in chunk order (deterministic; no atomics, unlike the reference's `omp atomic`, opt_coo.cpp:34-46).
+// Sums are re-associated across lanes: y is within the 1e-12 tolerance, not bit-identical to the CRS order (the
+// reference's own COO order is not defined either).  options.coo_path = 1 keeps the order-preserving tile kernel.
+constexpr int CS_THREADS = 256;
+
+template <int E>
+__global__ void __launch_bounds__(CS_THREADS)
+coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
+                  const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
+                  int nTiles)
+{
+    constexpr int CHUNK = E / (CS_THREADS / 32);              // entries per warp and tile
+    constexpr int GROUPS = CHUNK / 128;
+    extern __shared__ __align__(128) unsigned char cs_smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    int *srow = reinterpret_cast<int *>(cs_smem);             // [2][E]
+    int *scol = srow + 2 * E;                                 // [2][E]
+    double *sval = reinterpret_cast<double *>(scol + 2 * E);  // [2][E]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
+
+    auto issue = [&](int s, int t) {                          // thread 0 only
+        const long long t0 = (long long)t * E;
+        const int n = (int)min((long long)E, (long long)nnz - t0);
+        const uint32_t b4 = (uint32_t)((n * 4 + 15) & ~15), b8 = (uint32_t)(n * 8 + 15) & ~15u;   // allocations carry slack
+        mbar_expect_tx(&bar[s], 2 * b4 + b8);
+        tma_load_1d(srow + s * E, row + t0, b4, &bar[s], pol_stream);
+        tma_load_1d(scol + s * E, col + t0, b4, &bar[s], pol_stream);
+        tma_load_1d(sval + s * E, val + t0, b8, &bar[s], pol_stream);
+    };
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        if ((int)blockIdx.x < nTiles) issue(0, blockIdx.x);
+        if ((int)(blockIdx.x + gridDim.x) < nTiles) issue(1, blockIdx.x + gridDim.x);
+    }
+    int k = 0;
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x, k++) {
+        const int s = k & 1;
+        const long long t0 = (long long)t * E;
+        const int n = (int)min((long long)E, (long long)nnz - t0);
+        const int c0 = warp * CHUNK;                          // this warp's chunk inside the tile
+        // row id in front of the chunk: shared memory, or (first warp) the last entry of the previous tile
+        int before = -1;
+        if (lane == 0 && warp == 0 && t0 > 0) before = row[t0 - 1];
+        mbar_wait(&bar[s], (uint32_t)(k >> 1) & 1u);
+        const int *R = srow + s * E, *Cc = scol + s * E;
+        const double *V = sval + s * E;
+        if (c0 < n) {
+            if (lane == 0 && warp > 0) before = R[c0 - 1];
+            before = __shfl_sync(0xffffffffu, before, 0);
+            const int rowBefore = before;
+            bool started = false;                             // a run has started in this chunk (else: still the carried-in piece)
+            double cin = 0.0;                                 // sum of the open run so far (or of the carried-in piece)
+            int lastRow = before;
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
+                const int e = c0 + g * 128 + 4 * lane;
+                if (c0 + g * 128 >= n) break;
+                int4 r;
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                if (e + 3 < n) {
+                    r = *reinterpret_cast<const int4 *>(R + e);
+                    const int4 c = *reinterpret_cast<const int4 *>(Cc + e);
+                    const double2 v0 = *reinterpret_cast<const double2 *>(V + e), v1 = *reinterpret_cast<const double2 *>(V + e + 2);
+                    const double x0 = ld_x(x + c.x, pol_x), x1 = ld_x(x + c.y, pol_x), x2 = ld_x(x + c.z, pol_x), x3 = ld_x(x + c.w, pol_x);
+                    p0 = __dmul_rn(v0.x, x0); p1 = __dmul_rn(v0.y, x1); p2 = __dmul_rn(v1.x, x2); p3 = __dmul_rn(v1.y, x3);
+                } else {                                      // ragged end of the last tile: missing entries repeat the last row with product 0
+                    const int last = R[n - 1];
+                    r.x = e < n ? R[e] : last; r.y = e + 1 < n ? R[e + 1] : last; r.z = e + 2 < n ? R[e + 2] : last; r.w = last;
+                    if (e < n) p0 = __dmul_rn(V[e], ld_x(x + Cc[e], pol_x));
+                    if (e + 1 < n) p1 = __dmul_rn(V[e + 1], ld_x(x + Cc[e + 1], pol_x));
+                    if (e + 2 < n) p2 = __dmul_rn(V[e + 2], ld_x(x + Cc[e + 2], pol_x));
+                }
+                int rprev = __shfl_up_sync(0xffffffffu, r.w, 1);
+                if (lane == 0) rprev = lastRow;
+                const bool b0 = r.x != rprev, b1 = r.y != r.x, b2 = r.z != r.y, b3 = r.w != r.z;
+                const bool has = b0 | b1 | b2 | b3;
+                // runs inside the lane: head = entries before the first start, tail = entries from the last start on
+                double head = 0.0, acc = 0.0;
+                bool seen = false;
+                auto step = [&](bool b, int rp, int rc, double p) {
+                    if (b) {
+                        if (!seen) head = acc;
+                        else y[rp] = acc;                     // a run that started and ended in this lane
+                        for (int z = rp + 1; z < rc; z++) y[z] = 0.0;      // empty rows in front of the new run (beta = 0)
+                        seen = true;
+                        acc = p;
+                    } else acc = __dadd_rn(acc, p);
+                };
+                step(b0, rprev, r.x, p0); step(b1, r.x, r.y, p1); step(b2, r.y, r.z, p2); step(b3, r.z, r.w, p3);
+                // segmented inclusive scan over the lanes: segments begin at lanes that hold a run start
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                const unsigned below = m & (0xffffffffu >> (31 - lane));           // starts at or below this lane
+                const int seg = below ? 31 - __clz(below) : 0;
+                double v = acc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double u = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane - d >= seg) v = __dadd_rn(v, u);
+                }
+                if (!below) v = __dadd_rn(v, cin);                                  // still the run that was open when the group began
+                double excl = __shfl_up_sync(0xffffffffu, v, 1);
+                if (lane == 0) excl = cin;
+                if (has) {
+                    // this lane's first start closes the run that was open in front of it
+                    const double total = __dadd_rn(excl, head);
+                    const bool firstInChunk = !started && !(m & ((1u << lane) - 1u));
+                    if (!firstInChunk) y[rprev] = total;
+                    else if (!(g == 0 && lane == 0 && b0))        // the piece in front of the chunk's first start continues an earlier
+                        carry[(long long)t * (CS_THREADS / 32) + warp] = total;   // chunk's run (empty if the chunk begins with a start)
+                }
+                cin = __shfl_sync(0xffffffffu, v, 31);
+                lastRow = __shfl_sync(0xffffffffu, r.w, 31);
+                started = started || m != 0u;
+            }
+            if (lane == 0) {
+                if (started) y[lastRow] = cin;                // the run still open at the end of the chunk: it started here
+                else carry[(long long)t * (CS_THREADS / 32) + warp] = cin;         // the whole chunk belongs to an earlier run
+            }
+            // trailing empty rows after the very last entry
+            if (t0 + n == nnz && c0 + CHUNK >= n)
+                for (int z = lastRow + 1 + lane; z < nRow; z += 32) y[z] = 0.0;
+        }
+        __syncthreads();                                      // every warp is done with stage s
+        if (tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
+    }
+}
+
+// one thread per chunk: adds the carried-in pieces of a run that crosses chunk boundaries, in chunk order
+__global__ void coo_stream_fixup_kernel(const int *__restrict__ row, double *__restrict__ y, const double *__restrict__ carry,
+                                        int nnz, int chunk, int nChunks)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < 1 || c >= nChunks) return;
+    const long long c0 = (long long)c * chunk;
+    const int rc = row[c0];
+    if (row[c0 - 1] != rc) return;                            // a run starts exactly at the chunk start
+    const long long p0 = c0 - chunk;                          // the chunk in front merely passes the run through: not the first piece
+    if (row[p0] == rc && p0 > 0 && row[p0 - 1] == rc) return;
+    double sum = 0.0;
+    for (int u = c; u < nChunks && row[(long long)u * chunk] == rc; u++) sum = __dadd_rn(sum, carry[u]);
+    y[rc] = __dadd_rn(y[rc], sum);
+}
+
 struct CooFormat : Format {
     DevBuf<int> row, col;
     DevBuf<double> val, carry;
     int nTiles = 0;
+    int path = 0;                                             // 0 = entry stream (coo_stream_kernel), 1 = order-preserving tile kernel
+    int E = 2048;                                             // entry stream: entries per tile
+    explicit CooFormat(int path_) : path(path_) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
         nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
         B2_TRY(validate_sorted_coo(A, s));
-        B2_TRY(row.alloc((size_t)nnz));
-        B2_TRY(col.alloc((size_t)nnz));
-        B2_TRY(val.alloc((size_t)nnz));
-        B2_CUDA(cudaMemcpyAsync(row.p, A.row, row.bytes(), cudaMemcpyDeviceToDevice, s));   // opt_coo.cpp:14-19
-        B2_CUDA(cudaMemcpyAsync(col.p, A.col, col.bytes(), cudaMemcpyDeviceToDevice, s));
-        B2_CUDA(cudaMemcpyAsync(val.p, A.val, val.bytes(), cudaMemcpyDeviceToDevice, s));
-        nTiles = ceil_div(nnz, COO_TILE);
-        B2_TRY(carry.alloc((size_t)nTiles));
+        // 8 entries of slack: the bulk copies of the last tile are rounded up to 16 bytes
+        B2_TRY(row.alloc((size_t)nnz + 8));
+        B2_TRY(col.alloc((size_t)nnz + 8));
+        B2_TRY(val.alloc((size_t)nnz + 8));
+        B2_CUDA(cudaMemsetAsync(row.p + nnz, 0, 8 * sizeof(int), s));
+        B2_CUDA(cudaMemsetAsync(col.p + nnz, 0, 8 * sizeof(int), s));
+        B2_CUDA(cudaMemsetAsync(val.p + nnz, 0, 8 * sizeof(double), s));
+        B2_CUDA(cudaMemcpyAsync(row.p, A.row, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));   // opt_coo.cpp:14-19
+        B2_CUDA(cudaMemcpyAsync(col.p, A.col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(cudaMemcpyAsync(val.p, A.val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+        static const char *env_path = getenv("B200SPMV_COO_PATH");
+        static const int env_e = getenv("B200SPMV_COO_E") ? atoi(getenv("B200SPMV_COO_E")) : 0;
+        if (env_path) path = strcmp(env_path, "tile") == 0 ? 1 : 0;
+        E = env_e == 1024 ? 1024 : 2048;
+        nTiles = ceil_div(nnz, path == 1 ? COO_TILE : E);
+        B2_TRY(carry.alloc(path == 1 ? (size_t)nTiles : (size_t)nTiles * (CS_THREADS / 32)));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
@@ -195,10 +367,42 @@ struct CooFormat : Format {
             B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
             return B200SPMV_OK;
         }
+        if (path != 1) return E == 1024 ? stream_multiply<1024>(x, y, s) : stream_multiply<2048>(x, y, s);
         coo_tile_kernel<false><<<nTiles, COO_THREADS, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, 1);
         B2_KERNEL_CHECK();
         if (nTiles > 1) {
             coo_fixup_kernel<false><<<ceil_div(nTiles, 256), 256, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nTiles);
+            B2_KERNEL_CHECK();
+        }
+        return B200SPMV_OK;
+    }
+
+    template <int TE> int stream_multiply(const double *x, double *y, cudaStream_t s)
+    {
+        constexpr size_t smem = 32 * (size_t)TE;
+        auto kern = coo_stream_kernel<TE>;
+        static std::map<int, int> per_sm;                      // resident CTAs per SM of this instantiation, by device
+        static int sms = 0;
+        static const int env_b = getenv("B200SPMV_COO_CTAS") ? atoi(getenv("B200SPMV_COO_CTAS")) : 0;
+        int dev = 0;
+        B2_CUDA(cudaGetDevice(&dev));
+        if (!sms) B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        auto it = per_sm.find(dev);
+        if (it == per_sm.end()) {
+            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int n = 0;
+            B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, CS_THREADS, smem));
+            if (n < 1) { set_error("COO entry stream: %zu bytes of shared memory do not fit", smem); return B200SPMV_ERR_UNSUPPORTED; }
+            it = per_sm.emplace(dev, n).first;
+        }
+        const int perSm = env_b > 0 ? std::min(env_b, it->second) : it->second;
+        const int grid = std::min(nTiles, sms * perSm);
+        kern<<<grid, CS_THREADS, smem, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, nTiles);
+        B2_KERNEL_CHECK();
+        constexpr int chunk = TE / (CS_THREADS / 32);
+        const int nChunks = ceil_div(nnz, chunk);
+        if (nChunks > 1) {
+            coo_stream_fixup_kernel<<<ceil_div(nChunks, 256), 256, 0, s>>>(row.p, y, carry.p, nnz, chunk, nChunks);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -210,21 +414,22 @@ struct CooFormat : Format {
             *out = 16LL * nnz + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = nTiles > 1 ? 2 : 1; return true; }
+        if (n == "launches") { *out = nTiles > 1 || path != 1 ? 2 : 1; return true; }
         if (n == "nTiles") { *out = nTiles; return true; }
+        if (n == "coo_path") { *out = path; return true; }
         return false;
     }
 
     long long array(const std::string &n, void *dst, long long cap) override
     {
-        if (n == "row_idx") return export_device(row.p, row.bytes(), dst, cap);
-        if (n == "col_idx") return export_device(col.p, col.bytes(), dst, cap);
-        if (n == "val") return export_device(val.p, val.bytes(), dst, cap);
+        if (n == "row_idx") return export_device(row.p, sizeof(int) * (size_t)nnz, dst, cap);
+        if (n == "col_idx") return export_device(col.p, sizeof(int) * (size_t)nnz, dst, cap);
+        if (n == "val") return export_device(val.p, sizeof(double) * (size_t)nnz, dst, cap);
         return -1000;
     }
 };
 
-Format *make_coo(const b200spmv_options &) { return new CooFormat(); }
+Format *make_coo(const b200spmv_options &o) { return new CooFormat(o.coo_path); }
 
 // y[r] continues with the sorted triplets' products, run by run (HYB's COO tail, hyb.cu); carry: ceil(nnz / COO_TILE) doubles
 int coo_accumulate(const int *row, const int *col, const double *val, int nnz, int nRow, const double *x, double *y,

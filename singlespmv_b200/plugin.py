@@ -109,12 +109,12 @@ class SpMatOpt:
     ``scalar(name)`` / ``array(name, dtype)`` read the fields back under the reference's names, in the
     reference's logical layout, for parity checks."""
 
-    def __init__(self, fmt, segment_width=0, n_block=0, csr5_sigma=0, ss_faithful=0, value_f32=0, crs_path=0, profile=0, col_blocks=0, hyb_k=0, precision=0):
+    def __init__(self, fmt, segment_width=0, n_block=0, csr5_sigma=0, ss_faithful=0, value_f32=0, crs_path=0, profile=0, col_blocks=0, hyb_k=0, precision=0, coo_path=0):
         self.fmt = fmt
         o = Options()
         o.segment_width, o.n_block, o.csr5_sigma, o.ss_faithful = segment_width, n_block, csr5_sigma, ss_faithful
         o.value_f32, o.crs_path, o.profile, o.col_blocks = value_f32, crs_path, profile, col_blocks
-        o.hyb_k, o.precision = hyb_k, precision
+        o.hyb_k, o.precision, o.coo_path = hyb_k, precision, coo_path
         self.h = C.c_void_p()
         check(lib.b200spmv_create(FORMATS[fmt], C.byref(o), C.byref(self.h)))
         self.nRow = self.nCol = self.nNnz = 0

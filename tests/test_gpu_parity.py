@@ -231,11 +231,17 @@ def test_ell_golden(sp, name):
 def test_coo(sp, oracle, all_cases):
     for name, nRow, nCol, row, col, val, x in all_cases:
         y_ref = oracle.crs_result(nRow, row, col, val, x)
+        # default: the entry stream (segmented warp scans re-associate the sums: tolerance, deterministic)
         A_opt, y = run_host(sp, "coo", nRow, nCol, row, col, val, x)
         assert np.array_equal(A_opt.array("row_idx", np.int32), row), name      # opt_coo.cpp:14-19 aliases the input
         assert np.array_equal(A_opt.array("col_idx", np.int32), col), name
         assert np.array_equal(A_opt.array("val", np.float64), val), name
         assert A_opt.scalar("alg_bytes") == 16 * len(row) + 8 * nCol + 8 * nRow
+        assert A_opt.scalar("coo_path") == 0
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        # coo_path = 1: the order-preserving tile kernel
+        A_opt, y = run_host(sp, "coo", nRow, nCol, row, col, val, x, coo_path=1)
+        assert A_opt.scalar("coo_path") == 1
         assert_y(y, y_ref, row, col, val, x, nRow)
         short = np.bincount(row, minlength=nRow) <= 64
         assert np.array_equal(y[short], y_ref[short]), name                     # serial order == the verifier's (util.cpp:67-72)
@@ -252,11 +258,36 @@ def test_coo_tile_boundaries(sp, oracle):
         val = rng.standard_normal(len(row))
         x = rng.random(nCol)
         y_ref = oracle.crs_result(nRow, row, col, val, x)
-        for fmt in ("coo", "crs", "ss"):
-            _, y = run_host(sp, fmt, nRow, nCol, row, col, val, x)
+        for fmt, opt in (("coo", {"coo_path": 1}), ("crs", {}), ("ss", {})):
+            _, y = run_host(sp, fmt, nRow, nCol, row, col, val, x, **opt)
             assert_y(y, y_ref, row, col, val, x, nRow)
             short = np.array(lens) <= 64
             assert np.array_equal(y[short], y_ref[short]), (fmt, lens[:4])
+        _, y = run_host(sp, "coo", nRow, nCol, row, col, val, x)
+        assert_y(y, y_ref, row, col, val, x, nRow)
+
+
+def test_coo_entry_stream_chunk_boundaries(sp, oracle):
+    """The entry stream's units: 4 entries per lane, 128 per warp pass, 256 per warp chunk, 2048 per tile.  Runs that start or
+    end exactly on each of them, runs that pass through whole chunks and tiles, single-entry rows, empty-row gaps, ragged ends."""
+    rng = np.random.default_rng(11)
+    shapes = ([4] * 64 + [128] * 3 + [256, 256, 1, 255, 2048, 2047, 1, 1, 4096 + 256, 3],
+              [1] * 5000,
+              [0, 0, 3, 0, 125, 0, 0, 128, 1, 0, 255, 257, 0, 0, 0, 6000, 0, 2, 0, 0],
+              [7] * 3000 + [0] * 9,
+              [300] * 40 + [5] * 13,
+              [1, 2047, 2048 * 5, 1])
+    for lens in shapes:
+        nRow, nCol = len(lens), 12000
+        row = np.repeat(np.arange(nRow), lens).astype(np.int32)
+        col = np.concatenate([np.sort(rng.choice(nCol, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+        val = rng.standard_normal(len(row))
+        x = rng.random(nCol)
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        _, y = run_host(sp, "coo", nRow, nCol, row, col, val, x)
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        empty = np.array(lens) == 0
+        assert np.all(y[empty] == 0.0)
 
 
 # ------------------------------------------------------------------------------------------ JDS
@@ -711,7 +742,10 @@ def test_full_size_stencils(sp, kind, p0, fmts):
         assert torch.allclose(lin, 2.0 * ys[f] + 0.5 * _mult(m, z, n), rtol=1e-12, atol=1e-12), f
     first = fmts[0]
     for f in fmts[1:]:
-        assert torch.equal(ys[f], ys[first]), (f, first)
+        if f == "coo":                 # the entry stream re-associates the sums across lanes
+            assert torch.allclose(ys[f], ys[first], rtol=1e-12, atol=1e-13), (f, first)
+        else:
+            assert torch.equal(ys[f], ys[first]), (f, first)
 
 
 def test_full_size_uniform_and_rmat(sp, oracle):
