@@ -5,7 +5,12 @@
 #include "common.cuh"
 
 namespace b2 {
+Format *make_format(int format, const b200spmv_options &o);
 const char *last_error_cstr();
+// blocked.cu: more than 2^31-1 entries (or B200SPMV_BLOCK_NNZ) -> contiguous row blocks of the requested format
+int convert_row_blocked(int format, const b200spmv_options &opt, int nRow, int nCol, long long nnz, const int *row_d,
+                        const int *col_d, const double *val_d, cudaStream_t s, std::unique_ptr<Format> &out);
+long long row_block_limit();
 }
 using namespace b2;
 
@@ -23,7 +28,7 @@ struct b200spmv_matrix {
     int format = 0;
     b200spmv_options opt{};
     std::unique_ptr<Format> impl;
-    bool converted = false;
+    bool converted = false, blocked = false;
     // plan of the host-semantics pipeline (built on first use)
     int plan_chunks = 0, plan_pieces = 0;
     int chunk_rb[B200SPMV_HOST_CHUNKS + 1] = {}, chunk_need[B200SPMV_HOST_CHUNKS] = {};
@@ -44,7 +49,7 @@ struct b200spmv_matrix {
     }
 };
 
-static Format *make_format(int format, const b200spmv_options &o)
+Format *b2::make_format(int format, const b200spmv_options &o)
 {
     switch (format) {
     case B200SPMV_CRS: return make_crs(o);
@@ -155,15 +160,24 @@ int b200spmv_convert_coo_device(b200spmv_matrix *m, int nRow, int nCol, long lon
 {
     clear_error();
     if (!m) { set_error("convert: NULL handle"); return B200SPMV_ERR_INVALID; }
-    if (nRow < 0 || nCol < 0 || nnz < 0 || nnz > 0x7fffffffLL) {
-        set_error("convert: dimensions out of int32 range (nRow=%d nCol=%d nnz=%lld); the reference is int32 too (src/util.h:8)", nRow, nCol, nnz);
-        return B200SPMV_ERR_INVALID;
-    }
+    if (nRow < 0 || nCol < 0 || nnz < 0) { set_error("convert: negative dimension (nRow=%d nCol=%d nnz=%lld)", nRow, nCol, nnz); return B200SPMV_ERR_INVALID; }
     if (nnz > 0 && (!row_d || !col_d || !val_d)) { set_error("convert: NULL COO array"); return B200SPMV_ERR_INVALID; }
     B2_TRY(require_device());
-    CooView A{nRow, nCol, (int)nnz, row_d, col_d, val_d};
     m->converted = false;
     m->plan_chunks = m->plan_pieces = 0;
+    if (nnz > row_block_limit()) {
+        // beyond the reference's int32 entry count (src/util.h:8): row blocks with 32-bit offsets each (blocked.cu)
+        std::unique_ptr<Format> f;
+        B2_TRY(convert_row_blocked(m->format, m->opt, nRow, nCol, nnz, row_d, col_d, val_d, (cudaStream_t)stream, f));
+        m->impl = std::move(f);
+        m->blocked = m->converted = true;
+        return B200SPMV_OK;
+    }
+    if (m->blocked) {
+        m->impl.reset(make_format(m->format, m->opt));
+        m->blocked = false;
+    }
+    CooView A{nRow, nCol, (int)nnz, row_d, col_d, val_d};
     int st = m->impl->convert(A, (cudaStream_t)stream);
     if (st == B200SPMV_OK) m->converted = true;
     return st;
@@ -174,7 +188,7 @@ int b200spmv_convert_coo_host(b200spmv_matrix *m, int nRow, int nCol, long long 
 {
     clear_error();
     if (!m) { set_error("convert: NULL handle"); return B200SPMV_ERR_INVALID; }
-    if (nnz < 0 || nnz > 0x7fffffffLL) { set_error("convert: nnz=%lld out of int32 range", nnz); return B200SPMV_ERR_INVALID; }
+    if (nnz < 0) { set_error("convert: nnz=%lld", nnz); return B200SPMV_ERR_INVALID; }
     if (nnz > 0 && (!row_h || !col_h || !val_h)) { set_error("convert: NULL COO array"); return B200SPMV_ERR_INVALID; }
     B2_TRY(require_device());
     DevBuf<int> r, c;
@@ -390,7 +404,7 @@ int b200spmv_get_scalar(b200spmv_matrix *m, const char *name, long long *out)
     Format *f = m->impl.get();
     if (n == "nRow") { *out = f->nRow; return B200SPMV_OK; }
     if (n == "nCol") { *out = f->nCol; return B200SPMV_OK; }
-    if (n == "nNnz") { *out = f->nnz; return B200SPMV_OK; }
+    if (n == "nNnz") { if (!f->scalar(n, out)) *out = f->nnz; return B200SPMV_OK; }
     if (n == "format") { *out = m->format; return B200SPMV_OK; }
     if (n == "has_rows") { *out = f->has_rows() ? 1 : 0; return B200SPMV_OK; }
     if (f->scalar(n, out)) return B200SPMV_OK;

@@ -187,6 +187,14 @@ __global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restr
 // Sums are re-associated across lanes: y is within the 1e-12 tolerance, not bit-identical to the CRS order (the
 // reference's own COO order is not defined either).  options.coo_path = 1 keeps the order-preserving tile kernel.
 constexpr int CS_THREADS = 256;
+constexpr int CS_WARPS = CS_THREADS / 32;
+
+struct CooChunkRec {            // what a warp reports about its chunk; combined by one thread after the tile's barrier
+    double piece;               // sum of the entries in front of the chunk's first run start (the whole chunk if it has none)
+    double tail;                // sum of the run still open at the end of the chunk (started here)
+    int tailRow;                // its row, -1 if no run starts in the chunk
+    int pad;
+};
 
 template <int E>
 __global__ void __launch_bounds__(CS_THREADS)
@@ -194,10 +202,12 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                   const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
                   int nTiles)
 {
-    constexpr int CHUNK = E / (CS_THREADS / 32);              // entries per warp and tile
+    constexpr int CHUNK = E / CS_WARPS;                       // entries per warp and tile
     constexpr int GROUPS = CHUNK / 128;
+    static_assert(GROUPS >= 1, "a warp pass covers 128 entries");
     extern __shared__ __align__(128) unsigned char cs_smem[];
     __shared__ __align__(8) uint64_t bar[2];
+    __shared__ CooChunkRec rec[2][CS_WARPS];
     int *srow = reinterpret_cast<int *>(cs_smem);             // [2][E]
     int *scol = srow + 2 * E;                                 // [2][E]
     double *sval = reinterpret_cast<double *>(scol + 2 * E);  // [2][E]
@@ -219,24 +229,28 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
         if ((int)blockIdx.x < nTiles) issue(0, blockIdx.x);
         if ((int)(blockIdx.x + gridDim.x) < nTiles) issue(1, blockIdx.x + gridDim.x);
     }
+    // row id in front of a tile (thread 0 keeps it; fetched one tile ahead so that nobody waits for it)
+    int tileBefore = -1;
+    if (tid == 0 && (int)blockIdx.x < nTiles && blockIdx.x > 0) tileBefore = row[(long long)blockIdx.x * E - 1];
     int k = 0;
     for (int t = blockIdx.x; t < nTiles; t += gridDim.x, k++) {
         const int s = k & 1;
         const long long t0 = (long long)t * E;
         const int n = (int)min((long long)E, (long long)nnz - t0);
         const int c0 = warp * CHUNK;                          // this warp's chunk inside the tile
-        // row id in front of the chunk: shared memory, or (first warp) the last entry of the previous tile
-        int before = -1;
-        if (lane == 0 && warp == 0 && t0 > 0) before = row[t0 - 1];
+        const int tNext = t + gridDim.x;
+        int nextBefore = -1;
+        if (tid == 0 && tNext < nTiles) nextBefore = row[(long long)tNext * E - 1];
         mbar_wait(&bar[s], (uint32_t)(k >> 1) & 1u);
         const int *R = srow + s * E, *Cc = scol + s * E;
         const double *V = sval + s * E;
         if (c0 < n) {
+            int before = tileBefore;
             if (lane == 0 && warp > 0) before = R[c0 - 1];
             before = __shfl_sync(0xffffffffu, before, 0);
-            const int rowBefore = before;
             bool started = false;                             // a run has started in this chunk (else: still the carried-in piece)
             double cin = 0.0;                                 // sum of the open run so far (or of the carried-in piece)
+            double piece = 0.0;
             int lastRow = before;
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
@@ -261,7 +275,7 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                 if (lane == 0) rprev = lastRow;
                 const bool b0 = r.x != rprev, b1 = r.y != r.x, b2 = r.z != r.y, b3 = r.w != r.z;
                 const bool has = b0 | b1 | b2 | b3;
-                // runs inside the lane: head = entries before the first start, tail = entries from the last start on
+                // runs inside the lane: head = entries before the first start, acc ends as the sum from the last start on
                 double head = 0.0, acc = 0.0;
                 bool seen = false;
                 auto step = [&](bool b, int rp, int rc, double p) {
@@ -292,39 +306,63 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                     const double total = __dadd_rn(excl, head);
                     const bool firstInChunk = !started && !(m & ((1u << lane) - 1u));
                     if (!firstInChunk) y[rprev] = total;
-                    else if (!(g == 0 && lane == 0 && b0))        // the piece in front of the chunk's first start continues an earlier
-                        carry[(long long)t * (CS_THREADS / 32) + warp] = total;   // chunk's run (empty if the chunk begins with a start)
+                    else piece = total;                       // continues a run of an earlier chunk (0 if the chunk begins with a start)
                 }
+                if (!started && m) piece = __shfl_sync(0xffffffffu, piece, __ffs(m) - 1);
                 cin = __shfl_sync(0xffffffffu, v, 31);
                 lastRow = __shfl_sync(0xffffffffu, r.w, 31);
                 started = started || m != 0u;
             }
             if (lane == 0) {
-                if (started) y[lastRow] = cin;                // the run still open at the end of the chunk: it started here
-                else carry[(long long)t * (CS_THREADS / 32) + warp] = cin;         // the whole chunk belongs to an earlier run
+                CooChunkRec q;
+                q.piece = started ? piece : cin;
+                q.tail = cin;
+                q.tailRow = started ? lastRow : -1;
+                q.pad = 0;
+                rec[s][warp] = q;
             }
             // trailing empty rows after the very last entry
             if (t0 + n == nnz && c0 + CHUNK >= n)
                 for (int z = lastRow + 1 + lane; z < nRow; z += 32) y[z] = 0.0;
         }
-        __syncthreads();                                      // every warp is done with stage s
+        __syncthreads();                                      // every warp is done with stage s, the chunk records are in place
         if (tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
+        if (tid == 32) {
+            // stitch the chunks of the tile: a chunk's leading piece belongs to the run open at the end of the chunk in front
+            // of it; the tile's own leading piece goes to carry[t] (fix-up kernel), runs that end inside the tile get their y
+            const int nw = min(CS_WARPS, (n + CHUNK - 1) / CHUNK);
+            double tilePiece = 0.0, acc = 0.0;
+            int accRow = -1;
+            for (int w = 0; w < nw; w++) {
+                const CooChunkRec q = rec[s][w];
+                if (accRow >= 0) acc = __dadd_rn(acc, q.piece);
+                else tilePiece = __dadd_rn(tilePiece, q.piece);
+                if (q.tailRow >= 0) {
+                    if (accRow >= 0) y[accRow] = acc;
+                    accRow = q.tailRow;
+                    acc = q.tail;
+                }
+            }
+            if (accRow >= 0) y[accRow] = acc;
+            carry[t] = tilePiece;
+        }
+        tileBefore = nextBefore;
     }
 }
 
-// one thread per chunk: adds the carried-in pieces of a run that crosses chunk boundaries, in chunk order
+// one thread per tile: adds the leading pieces of the tiles a run passes through to the y of the tile it started in, in tile order
 __global__ void coo_stream_fixup_kernel(const int *__restrict__ row, double *__restrict__ y, const double *__restrict__ carry,
-                                        int nnz, int chunk, int nChunks)
+                                        int nnz, int tile, int nTiles)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < 1 || c >= nChunks) return;
-    const long long c0 = (long long)c * chunk;
+    if (c < 1 || c >= nTiles) return;
+    const long long c0 = (long long)c * tile;
     const int rc = row[c0];
-    if (row[c0 - 1] != rc) return;                            // a run starts exactly at the chunk start
-    const long long p0 = c0 - chunk;                          // the chunk in front merely passes the run through: not the first piece
+    if (row[c0 - 1] != rc) return;                            // a run starts exactly at the tile start
+    const long long p0 = c0 - tile;                           // the tile in front merely passes the run through: not the first piece
     if (row[p0] == rc && p0 > 0 && row[p0 - 1] == rc) return;
     double sum = 0.0;
-    for (int u = c; u < nChunks && row[(long long)u * chunk] == rc; u++) sum = __dadd_rn(sum, carry[u]);
+    for (int u = c; u < nTiles && row[(long long)u * tile] == rc; u++) sum = __dadd_rn(sum, carry[u]);
     y[rc] = __dadd_rn(y[rc], sum);
 }
 
@@ -355,7 +393,7 @@ struct CooFormat : Format {
         if (env_path) path = strcmp(env_path, "tile") == 0 ? 1 : 0;
         E = env_e == 1024 ? 1024 : 2048;
         nTiles = ceil_div(nnz, path == 1 ? COO_TILE : E);
-        B2_TRY(carry.alloc(path == 1 ? (size_t)nTiles : (size_t)nTiles * (CS_THREADS / 32)));
+        B2_TRY(carry.alloc((size_t)nTiles));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
@@ -399,10 +437,8 @@ struct CooFormat : Format {
         const int grid = std::min(nTiles, sms * perSm);
         kern<<<grid, CS_THREADS, smem, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, nTiles);
         B2_KERNEL_CHECK();
-        constexpr int chunk = TE / (CS_THREADS / 32);
-        const int nChunks = ceil_div(nnz, chunk);
-        if (nChunks > 1) {
-            coo_stream_fixup_kernel<<<ceil_div(nChunks, 256), 256, 0, s>>>(row.p, y, carry.p, nnz, chunk, nChunks);
+        if (nTiles > 1) {
+            coo_stream_fixup_kernel<<<ceil_div(nTiles, 256), 256, 0, s>>>(row.p, y, carry.p, nnz, TE, nTiles);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -414,7 +450,7 @@ struct CooFormat : Format {
             *out = 16LL * nnz + 8LL * nCol + 8LL * nRow;
             return true;
         }
-        if (n == "launches") { *out = nTiles > 1 || path != 1 ? 2 : 1; return true; }
+        if (n == "launches") { *out = nTiles > 1 ? 2 : 1; return true; }
         if (n == "nTiles") { *out = nTiles; return true; }
         if (n == "coo_path") { *out = path; return true; }
         return false;

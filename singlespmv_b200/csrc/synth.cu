@@ -26,7 +26,8 @@ __host__ __device__ __forceinline__ double entry_value(uint64_t seed, int r, int
 // ---------------------------------------------------------------- stencils
 __device__ __forceinline__ int span(int i, int n) { return 1 + (i > 0) + (i < n - 1); }
 
-__global__ void stencil_count_kernel(int kind, int n, int rowBegin, int rows, int *__restrict__ cnt)
+template <typename OT>
+__global__ void stencil_count_kernel(int kind, int n, int rowBegin, int rows, OT *__restrict__ cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > rows) return;
@@ -41,13 +42,14 @@ __global__ void stencil_count_kernel(int kind, int n, int rowBegin, int rows, in
     }
 }
 
-__global__ void stencil_fill_kernel(int kind, int n, int rowBegin, int rows, const int *__restrict__ off,
+template <typename OT>
+__global__ void stencil_fill_kernel(int kind, int n, int rowBegin, int rows, const OT *__restrict__ off,
                                     int *__restrict__ row, int *__restrict__ col, double *__restrict__ val)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     const int r = rowBegin + i;
-    int at = off[i];
+    OT at = off[i];
     if (kind == B200SPMV_SYNTH_LAP2D5) {
         const int gi = r / n, gj = r % n;
         for (int di = -1; di <= 1; di++)
@@ -222,33 +224,38 @@ extern "C" int b200spmv_synth(int kind, long long p0, long long p1, unsigned lon
     if (kind == B200SPMV_SYNTH_UNIFORM) {
         if (p1 < 1 || p1 > UNIFORM_MAX_K || p1 > nRow) { set_error("synth UNIFORM: K=%lld must be in [1,%d] and <= nCol", p1, UNIFORM_MAX_K); return B200SPMV_ERR_INVALID; }
         const long long nnz = (long long)rows * p1;
-        if (nnz > 0x7fffffffLL) { set_error("synth UNIFORM: %lld entries exceed int32", nnz); return B200SPMV_ERR_INVALID; }
         B2_TRY(alloc_coo(out, nnz));
         if (rows) uniform_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(seed, nRow, (int)p1, rowBegin, rows, out->row_d, out->col_d, out->val_d);
         B2_KERNEL_CHECK();
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
+    // int32 offsets unless the requested rows can hold more than 2^31-1 entries (rows x longest row): then 64-bit
+    // offsets -- one GPU holds such a matrix easily (180 GB); the formats take it as row blocks (csrc/blocked.cu)
+    const long long perRow = kind == B200SPMV_SYNTH_LAP2D5 ? 5 : kind == B200SPMV_SYNTH_LAP3D7 ? 7 : 27;
+    if ((long long)rows * perRow > 0x7fffffffLL) {
+        DevBuf<long long> cnt;
+        B2_TRY(cnt.alloc((size_t)rows + 1));
+        stencil_count_kernel<long long><<<ceil_div((long long)rows + 1, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p);
+        B2_KERNEL_CHECK();
+        B2_TRY(exclusive_scan_i64(cnt.p, cnt.p, rows + 1, s));
+        long long nnz = 0;
+        B2_CUDA(cudaMemcpy(&nnz, cnt.p + rows, sizeof(long long), cudaMemcpyDeviceToHost));
+        B2_TRY(alloc_coo(out, nnz));
+        stencil_fill_kernel<long long><<<ceil_div(rows, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p, out->row_d, out->col_d, out->val_d);
+        B2_KERNEL_CHECK();
+        B2_CUDA(cudaStreamSynchronize(s));
+        return B200SPMV_OK;
+    }
     DevBuf<int> cnt;
     B2_TRY(cnt.alloc((size_t)rows + 1));
-    stencil_count_kernel<<<ceil_div((long long)rows + 1, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p);
+    stencil_count_kernel<int><<<ceil_div((long long)rows + 1, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p);
     B2_KERNEL_CHECK();
-    // int32 offsets are enough unless the SLICE itself exceeds 2^31-1 entries (the global matrix may be larger: a
-    // row-partitioned run only ever generates one block per GPU).  rows x longest row bounds the slice; only when
-    // that bound overflows is the exact 64-bit sum of the slice's row lengths taken.
-    {
-        const long long perRow = kind == B200SPMV_SYNTH_LAP2D5 ? 5 : kind == B200SPMV_SYNTH_LAP3D7 ? 7 : 27;
-        if ((long long)rows * perRow > 0x7fffffffLL) {
-            long long total = 0;
-            B2_TRY(sum_i32_as_i64(cnt.p, rows, &total, s));
-            if (total > 0x7fffffffLL) { set_error("synth: the requested rows hold %lld entries, more than int32", total); return B200SPMV_ERR_INVALID; }
-        }
-    }
     B2_TRY(exclusive_scan_i32(cnt.p, cnt.p, rows + 1, s));
     int nnz = 0;
     B2_CUDA(cudaMemcpy(&nnz, cnt.p + rows, sizeof(int), cudaMemcpyDeviceToHost));
     B2_TRY(alloc_coo(out, nnz));
-    if (rows) stencil_fill_kernel<<<ceil_div(rows, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p, out->row_d, out->col_d, out->val_d);
+    if (rows) stencil_fill_kernel<int><<<ceil_div(rows, 256), 256, 0, s>>>(kind, (int)p0, rowBegin, rows, cnt.p, out->row_d, out->col_d, out->val_d);
     B2_KERNEL_CHECK();
     B2_CUDA(cudaStreamSynchronize(s));
     return B200SPMV_OK;

@@ -785,6 +785,74 @@ def test_full_size_uniform_and_rmat(sp, oracle):
         d.free()
 
 
+# ------------------------------------------------------------------------------------------ beyond 2^31-1 entries on one GPU
+@pytest.mark.parametrize("fmt", ["crs", "coo", "ell", "jds", "dia", "ss", "css", "csr5", "hyb"])
+def test_row_blocked_matches_unblocked(sp, oracle, fmt, monkeypatch):
+    """csrc/blocked.cu with the block size forced down (B200SPMV_BLOCK_NNZ): the row blocks a matrix of more than 2^31-1
+    entries is cut into give the same y as the single matrix -- bit for bit, since rows are never split."""
+    import torch
+    cases_ = [oracle.stencil("lap3d7", 20), oracle.rmat(42, 11, 60000)] if fmt != "dia" else [oracle.stencil("lap3d7", 20)]
+    for nr, nc, row, col, val in cases_:
+        x = oracle.reference_vectors(nc, nr)[0]
+        A = sp.SpMat(nr, nc, row, col, val)
+        monkeypatch.delenv("B200SPMV_BLOCK_NNZ", raising=False)
+        whole = sp.SpMatOpt(fmt).convert_host(A)
+        monkeypatch.setenv("B200SPMV_BLOCK_NNZ", str(max(1000, len(row) // 5)))
+        cut = sp.SpMatOpt(fmt).convert_host(A)
+        monkeypatch.delenv("B200SPMV_BLOCK_NNZ", raising=False)
+        assert cut.scalar("row_blocks") >= 4 and cut.scalar("nNnz") == len(row) and cut.scalar("nRow") == nr
+        xd = torch.from_numpy(x).cuda()
+        ys = []
+        for m in (whole, cut):
+            y = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
+            m.multiply(xd.data_ptr(), y.data_ptr())
+            torch.cuda.synchronize()
+            ys.append(y.cpu().numpy())
+        y_ref = oracle.crs_result(nr, row, col, val, x)
+        assert_y(ys[1], y_ref, row, col, val, x, nr)
+        if fmt in ("crs", "ell", "jds", "dia", "ss"):          # one thread (or warp, in a fixed order) per row either way
+            assert np.array_equal(ys[0], ys[1]), fmt
+        if cut.scalar("has_rows"):
+            y = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
+            lo, hi = nr // 3, nr - nr // 7
+            cut.multiply_rows(lo, hi, xd.data_ptr(), y.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(y.cpu().numpy()[lo:hi], ys[1][lo:hi]) and bool(torch.isnan(y[:lo]).all()) and bool(torch.isnan(y[hi:]).all())
+        whole.destroy()
+        cut.destroy()
+
+
+def test_more_than_int32_entries_on_one_gpu(sp):
+    """2.6 G entries (uniform, 2^26 rows x 40): beyond the reference's int nNnz (src/util.h:8).  Checked through the
+    closed form of A.1 (every row sums its own 40 values: compared with a block-wise recomputation from the COO
+    arrays) and linearity."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150 * (1 << 30):
+        pytest.skip("needs ~120 GB of device memory")
+    d = sp.DeviceCoo("uniform", 1 << 26, 40, 1)
+    assert d.nNnz == (1 << 26) * 40 > 2 ** 31
+    m = sp.SpMatOpt("crs").convert_device(d)
+    assert m.scalar("nNnz") == d.nNnz and m.scalar("row_blocks") >= 2
+    n = d.nRow
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    y1 = _mult(m, ones, n)
+    # row sums straight from the COO values: rows have exactly 40 consecutive entries
+    from singlespmv_b200.dist import _DevArray
+    vals = torch.as_tensor(_DevArray(d.c.val_d, d.nNnz), device="cuda").view(n, 40)
+    acc = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for k in range(40):                                        # ascending column order, like the kernel
+        acc += vals[:, k]
+    assert torch.equal(y1, acc)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    y = _mult(m, x, n)
+    y2 = _mult(m, 2.0 * x, n)
+    assert torch.equal(y2, 2.0 * y) and bool(torch.isfinite(y).all())
+    m.destroy()
+    d.free()
+
+
 # ------------------------------------------------------------------------------------------ round 2 additions
 def _short_row_matrix(rng, nRow, nCol, max_len):
     """Rows of 0..max_len entries (many empty, many full), sorted, duplicate-free."""
