@@ -1,7 +1,7 @@
 # Round 2, GPU call 9 (1 GPU): COO entry stream with in-CTA stitching + prefetched tile-front row; launch list.
 mkdir -p gpurun_out
 TAG=r2c9
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coo or hyb" > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "coo or hyb or row_blocked or int32_entries" > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
 tail -4 gpurun_out/pytest_$TAG.log
 b() { # tag, env..., -- bench args
   tag=$1; shift

@@ -206,7 +206,10 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
     constexpr int GROUPS = CHUNK / 128;
     static_assert(GROUPS >= 1, "a warp pass covers 128 entries");
     extern __shared__ __align__(128) unsigned char cs_smem[];
-    __shared__ __align__(8) uint64_t bar[2];
+    // full[s]: the bulk copies of stage s have landed.  One CTA barrier per tile hands the stage back to the copy engine; a
+    // variant without it (per-warp release through a second mbarrier, the last warp stitching) let the warps drift apart and
+    // was 20 % slower on c5 (0.645 against 0.804 of the roofline, profiles/r2_experiments.md)
+    __shared__ __align__(8) uint64_t full[2];
     __shared__ CooChunkRec rec[2][CS_WARPS];
     int *srow = reinterpret_cast<int *>(cs_smem);             // [2][E]
     int *scol = srow + 2 * E;                                 // [2][E]
@@ -218,12 +221,12 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
         const long long t0 = (long long)t * E;
         const int n = (int)min((long long)E, (long long)nnz - t0);
         const uint32_t b4 = (uint32_t)((n * 4 + 15) & ~15), b8 = (uint32_t)(n * 8 + 15) & ~15u;   // allocations carry slack
-        mbar_expect_tx(&bar[s], 2 * b4 + b8);
-        tma_load_1d(srow + s * E, row + t0, b4, &bar[s], pol_stream);
-        tma_load_1d(scol + s * E, col + t0, b4, &bar[s], pol_stream);
-        tma_load_1d(sval + s * E, val + t0, b8, &bar[s], pol_stream);
+        mbar_expect_tx(&full[s], 2 * b4 + b8);
+        tma_load_1d(srow + s * E, row + t0, b4, &full[s], pol_stream);
+        tma_load_1d(scol + s * E, col + t0, b4, &full[s], pol_stream);
+        tma_load_1d(sval + s * E, val + t0, b8, &full[s], pol_stream);
     };
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
     __syncthreads();
     if (tid == 0) {
         if ((int)blockIdx.x < nTiles) issue(0, blockIdx.x);
@@ -238,13 +241,15 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
         const long long t0 = (long long)t * E;
         const int n = (int)min((long long)E, (long long)nnz - t0);
         const int c0 = warp * CHUNK;                          // this warp's chunk inside the tile
+        const int nGroups = c0 < n ? min(GROUPS, (n - c0 + 127) >> 7) : 0;
+        const int nw = min(CS_WARPS, (n + CHUNK - 1) / CHUNK);                      // warps with entries in this tile
         const int tNext = t + gridDim.x;
         int nextBefore = -1;
         if (tid == 0 && tNext < nTiles) nextBefore = row[(long long)tNext * E - 1];
-        mbar_wait(&bar[s], (uint32_t)(k >> 1) & 1u);
+        mbar_wait(&full[s], (uint32_t)(k >> 1) & 1u);
         const int *R = srow + s * E, *Cc = scol + s * E;
         const double *V = sval + s * E;
-        if (c0 < n) {
+        if (nGroups > 0) {
             int before = tileBefore;
             if (lane == 0 && warp > 0) before = R[c0 - 1];
             before = __shfl_sync(0xffffffffu, before, 0);
@@ -254,40 +259,53 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
             int lastRow = before;
 #pragma unroll
             for (int g = 0; g < GROUPS; g++) {
+                if (g >= nGroups) break;
                 const int e = c0 + g * 128 + 4 * lane;
-                if (c0 + g * 128 >= n) break;
-                int4 r;
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-                if (e + 3 < n) {
+                int4 r, c;
+                double2 v0, v1;
+                const bool fullGroup = c0 + g * 128 + 128 <= n;
+                if (fullGroup) {
                     r = *reinterpret_cast<const int4 *>(R + e);
-                    const int4 c = *reinterpret_cast<const int4 *>(Cc + e);
-                    const double2 v0 = *reinterpret_cast<const double2 *>(V + e), v1 = *reinterpret_cast<const double2 *>(V + e + 2);
-                    const double x0 = ld_x(x + c.x, pol_x), x1 = ld_x(x + c.y, pol_x), x2 = ld_x(x + c.z, pol_x), x3 = ld_x(x + c.w, pol_x);
-                    p0 = __dmul_rn(v0.x, x0); p1 = __dmul_rn(v0.y, x1); p2 = __dmul_rn(v1.x, x2); p3 = __dmul_rn(v1.y, x3);
-                } else {                                      // ragged end of the last tile: missing entries repeat the last row with product 0
+                    c = *reinterpret_cast<const int4 *>(Cc + e);
+                    v0 = *reinterpret_cast<const double2 *>(V + e);
+                    v1 = *reinterpret_cast<const double2 *>(V + e + 2);
+                } else {                                      // ragged end of the last tile: missing entries repeat the last row with value 0
                     const int last = R[n - 1];
-                    r.x = e < n ? R[e] : last; r.y = e + 1 < n ? R[e + 1] : last; r.z = e + 2 < n ? R[e + 2] : last; r.w = last;
-                    if (e < n) p0 = __dmul_rn(V[e], ld_x(x + Cc[e], pol_x));
-                    if (e + 1 < n) p1 = __dmul_rn(V[e + 1], ld_x(x + Cc[e + 1], pol_x));
-                    if (e + 2 < n) p2 = __dmul_rn(V[e + 2], ld_x(x + Cc[e + 2], pol_x));
+                    r.x = e < n ? R[e] : last; r.y = e + 1 < n ? R[e + 1] : last; r.z = e + 2 < n ? R[e + 2] : last; r.w = e + 3 < n ? R[e + 3] : last;
+                    c.x = e < n ? Cc[e] : 0; c.y = e + 1 < n ? Cc[e + 1] : 0; c.z = e + 2 < n ? Cc[e + 2] : 0; c.w = e + 3 < n ? Cc[e + 3] : 0;
+                    v0.x = e < n ? V[e] : 0.0; v0.y = e + 1 < n ? V[e + 1] : 0.0; v1.x = e + 2 < n ? V[e + 2] : 0.0; v1.y = e + 3 < n ? V[e + 3] : 0.0;
                 }
+                const double x0 = ld_x(x + c.x, pol_x), x1 = ld_x(x + c.y, pol_x), x2 = ld_x(x + c.z, pol_x), x3 = ld_x(x + c.w, pol_x);
+                const double p0 = __dmul_rn(v0.x, x0), p1 = __dmul_rn(v0.y, x1), p2 = __dmul_rn(v1.x, x2), p3 = __dmul_rn(v1.y, x3);
                 int rprev = __shfl_up_sync(0xffffffffu, r.w, 1);
                 if (lane == 0) rprev = lastRow;
                 const bool b0 = r.x != rprev, b1 = r.y != r.x, b2 = r.z != r.y, b3 = r.w != r.z;
                 const bool has = b0 | b1 | b2 | b3;
-                // runs inside the lane: head = entries before the first start, acc ends as the sum from the last start on
-                double head = 0.0, acc = 0.0;
-                bool seen = false;
-                auto step = [&](bool b, int rp, int rc, double p) {
-                    if (b) {
-                        if (!seen) head = acc;
-                        else y[rp] = acc;                     // a run that started and ended in this lane
-                        for (int z = rp + 1; z < rc; z++) y[z] = 0.0;      // empty rows in front of the new run (beta = 0)
-                        seen = true;
-                        acc = p;
-                    } else acc = __dadd_rn(acc, p);
-                };
-                step(b0, rprev, r.x, p0); step(b1, r.x, r.y, p1); step(b2, r.y, r.z, p2); step(b3, r.z, r.w, p3);
+                const int nStarts = (int)b0 + (int)b1 + (int)b2 + (int)b3;
+                // head = sum of the entries before the lane's first start, acc = sum from its last start on (all four
+                // entries if it has none).  Usual case -- at most one start per lane and no empty rows in between (rows are
+                // sorted: r.w - rprev counts the rows that begin here) -- without branches; the rest out of line.
+                double head, acc;
+                if (__any_sync(0xffffffffu, nStarts > 1 || r.w - rprev != nStarts)) {
+                    head = 0.0; acc = 0.0;
+                    bool seen = false;
+                    auto step = [&](bool b, int rp, int rc, double p) {
+                        if (b) {
+                            if (!seen) head = acc;
+                            else y[rp] = acc;                 // a run that started and ended in this lane
+#pragma unroll 1
+                            for (int z = rp + 1; z < rc; z++) y[z] = 0.0;  // empty rows in front of the new run (beta = 0)
+                            seen = true;
+                            acc = p;
+                        } else acc = __dadd_rn(acc, p);
+                    };
+                    step(b0, rprev, r.x, p0); step(b1, r.x, r.y, p1); step(b2, r.y, r.z, p2); step(b3, r.z, r.w, p3);
+                } else {
+                    // entries in front of the start go to head, the others to acc; adding 0.0 changes nothing
+                    const bool f0 = b0, f1 = f0 | b1, f2 = f1 | b2;                 // "a start at or before this entry"
+                    head = __dadd_rn(__dadd_rn((has && !f0) ? p0 : 0.0, (has && !f1) ? p1 : 0.0), (has && !f2) ? p2 : 0.0);
+                    acc = __dadd_rn(__dadd_rn(__dadd_rn((!has || f0) ? p0 : 0.0, (!has || f1) ? p1 : 0.0), (!has || f2) ? p2 : 0.0), p3);
+                }
                 // segmented inclusive scan over the lanes: segments begin at lanes that hold a run start
                 const unsigned m = __ballot_sync(0xffffffffu, has);
                 const unsigned below = m & (0xffffffffu >> (31 - lane));           // starts at or below this lane
@@ -313,6 +331,9 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                 lastRow = __shfl_sync(0xffffffffu, r.w, 31);
                 started = started || m != 0u;
             }
+            // trailing empty rows after the very last entry
+            if (t0 + n == nnz && c0 + CHUNK >= n)
+                for (int z = lastRow + 1 + lane; z < nRow; z += 32) y[z] = 0.0;
             if (lane == 0) {
                 CooChunkRec q;
                 q.piece = started ? piece : cin;
@@ -321,31 +342,29 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                 q.pad = 0;
                 rec[s][warp] = q;
             }
-            // trailing empty rows after the very last entry
-            if (t0 + n == nnz && c0 + CHUNK >= n)
-                for (int z = lastRow + 1 + lane; z < nRow; z += 32) y[z] = 0.0;
         }
+        // one thread stitches the chunks of the tile: a chunk's leading piece belongs to the run open at the end of the chunk in
+        // front of it; the tile's own leading piece goes to carry[t] (fix-up kernel), runs that end inside the tile get their y
         __syncthreads();                                      // every warp is done with stage s, the chunk records are in place
-        if (tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
         if (tid == 32) {
-            // stitch the chunks of the tile: a chunk's leading piece belongs to the run open at the end of the chunk in front
-            // of it; the tile's own leading piece goes to carry[t] (fix-up kernel), runs that end inside the tile get their y
-            const int nw = min(CS_WARPS, (n + CHUNK - 1) / CHUNK);
-            double tilePiece = 0.0, acc = 0.0;
+            double tilePiece = 0.0, a2 = 0.0;
             int accRow = -1;
             for (int w = 0; w < nw; w++) {
-                const CooChunkRec q = rec[s][w];
-                if (accRow >= 0) acc = __dadd_rn(acc, q.piece);
-                else tilePiece = __dadd_rn(tilePiece, q.piece);
-                if (q.tailRow >= 0) {
-                    if (accRow >= 0) y[accRow] = acc;
-                    accRow = q.tailRow;
-                    acc = q.tail;
+                const CooChunkRec *o = &rec[s][w];
+                const double oPiece = o->piece, oTail = o->tail;
+                const int oRow = o->tailRow;
+                if (accRow >= 0) a2 = __dadd_rn(a2, oPiece);
+                else tilePiece = __dadd_rn(tilePiece, oPiece);
+                if (oRow >= 0) {
+                    if (accRow >= 0) y[accRow] = a2;
+                    accRow = oRow;
+                    a2 = oTail;
                 }
             }
-            if (accRow >= 0) y[accRow] = acc;
+            if (accRow >= 0) y[accRow] = a2;
             carry[t] = tilePiece;
         }
+        if (tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
         tileBefore = nextBefore;
     }
 }
@@ -391,7 +410,8 @@ struct CooFormat : Format {
         static const char *env_path = getenv("B200SPMV_COO_PATH");
         static const int env_e = getenv("B200SPMV_COO_E") ? atoi(getenv("B200SPMV_COO_E")) : 0;
         if (env_path) path = strcmp(env_path, "tile") == 0 ? 1 : 0;
-        E = env_e == 1024 ? 1024 : 2048;
+        // tiles of 1024 entries (6 CTAs per SM) against 2048 (3 per SM): profiles/r2_experiments.md
+        E = env_e == 2048 ? 2048 : 1024;
         nTiles = ceil_div(nnz, path == 1 ? COO_TILE : E);
         B2_TRY(carry.alloc((size_t)nTiles));
         B2_CUDA(cudaStreamSynchronize(s));
@@ -433,7 +453,7 @@ struct CooFormat : Format {
             if (n < 1) { set_error("COO entry stream: %zu bytes of shared memory do not fit", smem); return B200SPMV_ERR_UNSUPPORTED; }
             it = per_sm.emplace(dev, n).first;
         }
-        const int perSm = env_b > 0 ? std::min(env_b, it->second) : it->second;
+        const int perSm = env_b > 0 ? std::min(env_b, it->second) : std::min(it->second, 6);
         const int grid = std::min(nTiles, sms * perSm);
         kern<<<grid, CS_THREADS, smem, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, nTiles);
         B2_KERNEL_CHECK();

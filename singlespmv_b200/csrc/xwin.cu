@@ -20,7 +20,7 @@ namespace {
 
 constexpr int XW_MAXPEERS = 64;
 constexpr size_t XW_HEADER = 4096;                 // flag words in front of x_ext (same allocation = one IPC handle)
-constexpr int XW_THREADS = 256;
+constexpr int XW_THREADS = 64;                     // small CTAs: they must fit into what the interior rows' persistent CTAs leave of an SM
 constexpr long long XW_SPIN_LIMIT = 4000000000LL;  // ~2 s of SM clocks: a rank that never shows up ends the kernel with an error flag
 
 struct XwHeader {                                  // lives at the start of every window
@@ -60,10 +60,9 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
 struct XwArgs {
     XwHeader *mine;                                // this rank's header
     char *const *peer_base;                        // [world] mapped window of every rank (own entry = own window)
-    const long long *peer_owned_off;               // [world] byte offset of the owned slice inside the peer's window
     const int *sources, *readers;                  // ranks this one pulls from / that pull from this one
     int nSources, nReaders, me;
-    const int *owner, *idx;                        // per halo entry: owning rank, index inside its owned slice
+    const double *const *src;                      // per halo entry: its address inside the owner's (mapped) slice
     int nHalo, nLeft, nLocal;
     double *x_ext;
 };
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(XW_THREADS) xwin_exchange_kernel(XwArgs a)
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = i0 + u * stride;
-            if (i < a.nHalo) v[u] = ld_peer(reinterpret_cast<const double *>(a.peer_base[a.owner[i]] + a.peer_owned_off[a.owner[i]]) + a.idx[i]);
+            if (i < a.nHalo) v[u] = ld_peer(a.src[i]);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -128,8 +127,9 @@ struct b200spmv_xwin {
     std::vector<long long> peerOwnedOff;           // bytes, from the peer's window base
     std::vector<bool> opened;
     DevBuf<char *> peer_d;
-    DevBuf<long long> off_d;
-    DevBuf<int> sources_d, readers_d, owner_d, idx_d;
+    DevBuf<const double *> src_d;
+    DevBuf<int> sources_d, readers_d;
+    int sms = 0;
     int nSources = 0, nReaders = 0, nHalo = 0, nLeft = 0, nLocal = 0;
     bool planned = false;
 };
@@ -226,14 +226,14 @@ int b200spmv_xwin_plan(b200spmv_xwin *w, const int *halo_cols_h, int nHalo, int 
     clear_error();
     if (!w || nHalo < 0 || (nHalo && !halo_cols_h) || !bounds_h || nReaders < 0 || (nReaders && !readers_h)) { set_error("xwin_plan: bad argument"); return B200SPMV_ERR_INVALID; }
     if ((long long)nLeft + nLocal + (nHalo - nLeft) != w->nExt || w->ownedOff != nLeft) { set_error("xwin_plan: the halo does not match the window layout"); return B200SPMV_ERR_INVALID; }
-    std::vector<int> owner((size_t)nHalo), idx((size_t)nHalo), sources;
+    std::vector<const double *> src((size_t)nHalo);
+    std::vector<int> sources;
     for (int i = 0; i < nHalo; i++) {
         const long long c = halo_cols_h[i];
         const int p = (int)(std::upper_bound(bounds_h, bounds_h + w->world + 1, c) - bounds_h) - 1;
         if (p < 0 || p >= w->world || p == w->rank) { set_error("xwin_plan: halo column %lld has no remote owner", c); return B200SPMV_ERR_INVALID; }
         if (!w->peer[(size_t)p]) { set_error("xwin_plan: the window of rank %d was not imported", p); return B200SPMV_ERR_STATE; }
-        owner[(size_t)i] = p;
-        idx[(size_t)i] = (int)(c - bounds_h[p]);
+        src[(size_t)i] = reinterpret_cast<const double *>(w->peer[(size_t)p] + w->peerOwnedOff[(size_t)p]) + (c - bounds_h[p]);
         if (sources.empty() || sources.back() != p) {
             if (std::find(sources.begin(), sources.end(), p) == sources.end()) sources.push_back(p);
         }
@@ -244,19 +244,14 @@ int b200spmv_xwin_plan(b200spmv_xwin *w, const int *halo_cols_h, int nHalo, int 
     w->nHalo = nHalo; w->nLeft = nLeft; w->nLocal = nLocal;
     w->nSources = (int)sources.size(); w->nReaders = nReaders;
     B2_TRY(w->peer_d.alloc((size_t)w->world));
-    B2_TRY(w->off_d.alloc((size_t)w->world));
     B2_TRY(w->sources_d.alloc(sources.size()));
     B2_TRY(w->readers_d.alloc((size_t)nReaders));
-    B2_TRY(w->owner_d.alloc((size_t)nHalo));
-    B2_TRY(w->idx_d.alloc((size_t)nHalo));
+    B2_TRY(w->src_d.alloc((size_t)nHalo));
+    B2_CUDA(cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, w->dev));
     B2_CUDA(cudaMemcpy(w->peer_d.p, w->peer.data(), sizeof(char *) * (size_t)w->world, cudaMemcpyHostToDevice));
-    B2_CUDA(cudaMemcpy(w->off_d.p, w->peerOwnedOff.data(), sizeof(long long) * (size_t)w->world, cudaMemcpyHostToDevice));
     if (!sources.empty()) B2_CUDA(cudaMemcpy(w->sources_d.p, sources.data(), sizeof(int) * sources.size(), cudaMemcpyHostToDevice));
     if (nReaders) B2_CUDA(cudaMemcpy(w->readers_d.p, readers_h, sizeof(int) * (size_t)nReaders, cudaMemcpyHostToDevice));
-    if (nHalo) {
-        B2_CUDA(cudaMemcpy(w->owner_d.p, owner.data(), sizeof(int) * (size_t)nHalo, cudaMemcpyHostToDevice));
-        B2_CUDA(cudaMemcpy(w->idx_d.p, idx.data(), sizeof(int) * (size_t)nHalo, cudaMemcpyHostToDevice));
-    }
+    if (nHalo) B2_CUDA(cudaMemcpy(w->src_d.p, src.data(), sizeof(const double *) * (size_t)nHalo, cudaMemcpyHostToDevice));
     w->planned = true;
     return B200SPMV_OK;
 }
@@ -269,14 +264,16 @@ int b200spmv_xwin_exchange(b200spmv_xwin *w, void *stream)
     XwArgs a;
     a.mine = reinterpret_cast<XwHeader *>(w->base);
     a.peer_base = w->peer_d.p;
-    a.peer_owned_off = w->off_d.p;
     a.sources = w->sources_d.p; a.readers = w->readers_d.p;
     a.nSources = w->nSources; a.nReaders = w->nReaders; a.me = w->rank;
-    a.owner = w->owner_d.p; a.idx = w->idx_d.p;
+    a.src = w->src_d.p;
     a.nHalo = w->nHalo; a.nLeft = w->nLeft; a.nLocal = w->nLocal;
     a.x_ext = reinterpret_cast<double *>(w->base + XW_HEADER);
-    // enough loads in flight to hide the NVLink round trip, few enough CTAs to leave the SMs to the interior rows
-    const int grid = std::max(1, std::min(32, ceil_div(w->nHalo, 4 * XW_THREADS)));
+    // The interior rows run as persistent CTAs that fill every SM up to a few thousand registers (chunk_stream: 5 x 256
+    // threads x 48 registers of 65536): CTAs of 64 threads x 32 registers still fit beside them, two per SM, whichever
+    // kernel the hardware (or a graph replay) starts first.  Measured with 256-thread CTAs: the exchange only ran after the
+    // interior rows had drained whenever it was launched second (2 GPUs, graph replay: 1.26 ms against 1.05).
+    const int grid = std::max(1, std::min(2 * w->sms, ceil_div(w->nHalo, 4 * XW_THREADS)));
     xwin_exchange_kernel<<<grid, XW_THREADS, 0, (cudaStream_t)stream>>>(a);
     B2_KERNEL_CHECK();
     return B200SPMV_OK;

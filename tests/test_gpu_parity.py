@@ -810,8 +810,9 @@ def test_row_blocked_matches_unblocked(sp, oracle, fmt, monkeypatch):
             ys.append(y.cpu().numpy())
         y_ref = oracle.crs_result(nr, row, col, val, x)
         assert_y(ys[1], y_ref, row, col, val, x, nr)
-        if fmt in ("crs", "ell", "jds", "dia", "ss"):          # one thread (or warp, in a fixed order) per row either way
-            assert np.array_equal(ys[0], ys[1]), fmt
+        if fmt in ("crs", "ell", "jds", "dia", "ss"):          # one thread per row of at most 64 entries either way
+            short = np.bincount(row, minlength=nr) <= 64
+            assert np.array_equal(ys[0][short], ys[1][short]), fmt
         if cut.scalar("has_rows"):
             y = torch.full((nr,), float("nan"), dtype=torch.float64, device="cuda")
             lo, hi = nr // 3, nr - nr // 7
