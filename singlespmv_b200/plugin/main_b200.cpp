@@ -187,7 +187,7 @@ int main (int argc, char **argv) {
     printf("%25s\t%lf\n", "KernelTime(us)", minElapsedTime * 1e6);
     printf("%25s\t%lld\n", "AlgBytes", algBytes);
     printf("%25s\t%lf\n", "EffectiveBW(GB/s)", gbs);
-    printf("%25s\t%lf\n", "RooflinePct(8000GB/s)", 100.0 * gbs / 8000.0);
+    printf("%25s\t%lf\n", "RooflinePct(8000GB/s)", 100.0 * gbs / (8000.0 * (A_opt.nGPU > 0 ? A_opt.nGPU : 1)));   // per GPU
     printf("%25s\t%lld\n", "LaunchesPerSpMV", B200Scalar(A_opt, "launches"));
     printf("%25s\t%lf\n", "ConvertTime(ms)", convertMs);
 #ifdef B200_DEVICE_RESIDENT

@@ -926,6 +926,44 @@ def test_ell_dense_row_never_reads_past_x(sp):
         assert np.array_equal(lcol[2], np.arange(nCol))                   # empty row: padding col = k (opt_ell.cpp:48)
 
 
+GUARD_FORMATS = [("crs", {}), ("crs", {"crs_path": 1}), ("coo", {}), ("coo", {"coo_path": 1}), ("ell", {}), ("jds", {}), ("dia", {}),
+                 ("ss", {}), ("css", {"n_block": 3}), ("csr5", {}), ("hyb", {}), ("ell", {"col_blocks": 3}), ("jds", {"col_blocks": 2})]
+
+
+@pytest.mark.parametrize("fmt,opt", GUARD_FORMATS)
+def test_guard_bands_around_x_and_y(sp, oracle, fmt, opt):
+    """Stand-in for compute-sanitizer memcheck (closed on this pool, profiles/r2_sanitizer.md): x lies between NaN bands and y
+    between canary bands inside larger buffers.  A gather outside x poisons y, a store outside y breaks a canary."""
+    import torch
+    G = 4096
+    mats = [oracle.stencil("lap3d7", 13), oracle.stencil("lap2d5", 37)]
+    if fmt != "dia":
+        mats += [oracle.rmat(7, 10, 30000), oracle.uniform(3, 3001, 2777, 9)]
+    for nr, nc, row, col, val in mats:
+        x = np.random.default_rng(nr).random(nc)
+        y_ref = oracle.crs_result(nr, row, col, val, x)
+        A = sp.SpMatOpt(fmt, **opt).convert_host(sp.SpMat(nr, nc, row, col, val))
+        xb = torch.full((nc + 2 * G,), float("nan"), dtype=torch.float64, device="cuda")
+        xb[G:G + nc] = torch.from_numpy(x).cuda()
+        yb = torch.full((nr + 2 * G,), -12345.0, dtype=torch.float64, device="cuda")
+        xp, yp = xb.data_ptr() + 8 * G, yb.data_ptr() + 8 * G
+        for _ in range(2):
+            A.multiply(xp, yp)
+        torch.cuda.synchronize()
+        assert bool((yb[:G] == -12345.0).all()) and bool((yb[G + nr:] == -12345.0).all()), (fmt, nr, "store outside y")
+        y = yb[G:G + nr].cpu().numpy()
+        assert np.all(np.isfinite(y)), (fmt, nr, "gather outside x")
+        assert_y(y, y_ref, row, col, val, x, nr)
+        if A.scalar("has_rows") and nr > 300:
+            lo, hi = 129, nr - 77
+            yb.fill_(-12345.0)
+            A.multiply_rows(lo, hi, xp, yp)
+            torch.cuda.synchronize()
+            assert bool((yb[:G + lo] == -12345.0).all()) and bool((yb[G + hi:] == -12345.0).all()), (fmt, nr, "row range")
+            assert np.array_equal(yb[G + lo:G + hi].cpu().numpy(), y[lo:hi])
+        A.destroy()
+
+
 @pytest.mark.parametrize("fmt,opt", [("crs", {}), ("crs", {"crs_path": 1}), ("css", {"n_block": 3}), ("ell", {}), ("dia", {}),
                                      ("ss", {})])
 def test_host_multiply_pipeline_pinned(sp, oracle, fmt, opt):
