@@ -451,6 +451,45 @@ def run_case(sp, torch, timer, wl_key, wl, fmt, options, coo, x_d, y_d, sptr, st
     return e, A
 
 
+def index64_case(sp, torch, timer, sptr, peak, mini):
+    """A matrix with more than 2^31-1 entries on ONE GPU (the reference's nNnz is an int, src/util.h:8; SURVEY.md 8f index
+    variant): 3-D 7-point Laplacian 700^3 = 343,000,000 rows, 2,398,060,000 nnz, CRS.  The library cuts it into row blocks with
+    32-bit offsets each (csrc/blocked.cu).  Checked on every row through the closed form of A.1."""
+    p0 = 40 if mini else 700
+    if mini:
+        os.environ["B200SPMV_BLOCK_NNZ"] = "100000"
+    try:
+        coo = sp.DeviceCoo("lap3d7", p0)
+        t0 = time.perf_counter()
+        A = sp.SpMatOpt("crs").convert_device(coo)
+        torch.cuda.synchronize()
+        t_conv = time.perf_counter() - t0
+        coo.free()
+    finally:
+        os.environ.pop("B200SPMV_BLOCK_NNZ", None)
+    n, nnz = A.nRow, A.nNnz
+    x_d = torch.ones(n, dtype=torch.float64, device="cuda")
+    y_d = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+
+    def step():
+        A.multiply(x_d.data_ptr(), y_d.data_ptr(), sptr)
+    ms = timer.run(step, 5, 3, False)
+    idx = torch.arange(n, device="cuda")
+
+    def span(a):
+        return 1 + (a > 0).to(torch.int8) + (a < p0 - 1).to(torch.int8)
+    cnt = span(idx // (p0 * p0)) + span((idx // p0) % p0) + span(idx % p0) - 2
+    del idx
+    ok = bool(torch.equal(y_d, (7 - cnt).double())) and int(cnt.sum(dtype=torch.int64).item()) == nnz
+    alg = A.scalar("alg_bytes")
+    e = {"workload": "CRS fp64, 3-D 7-point Laplacian %d^3 on one GPU" % p0, "nRow": n, "nnz": nnz, "beyond_int32": nnz > 2 ** 31 - 1,
+         "row_blocks": A.scalar("row_blocks"), "ms_per_step": ms, "gflops": 2.0 * nnz / (ms * 1e-3) / 1e9, "alg_bytes": alg,
+         "alg_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak, "convert_ms": t_conv * 1e3,
+         "check": "A.1 against the closed form on every row (exact small integers)", "ok": ok}
+    A.destroy()
+    return e
+
+
 def cusparse_compare(torch, coo, x_d, y_d, sptr, warmup, steps):
     """Comparison point only (libb200cmp.so, singlespmv_b200/compare/): cusparseSpMV CSR on the same device arrays
     (the reference's src/opt_cusparse.cpp:57-83 re-expressed for cuSPARSE 12)."""
@@ -659,6 +698,15 @@ def run_single(args, wl_key, only_format):
                 entry["error"] = repr(err)
             configs[key] = entry
         line["configs"] = configs
+        if args.configs == "all":
+            try:
+                A.destroy()
+                coo.free()
+                del x_d, y_d
+                torch.cuda.empty_cache()
+                line["index64"] = index64_case(sp, torch, timer, sptr, peak, args.mini)
+            except Exception as err:                         # noqa: BLE001
+                line["index64"] = {"error": repr(err)}
         if not args.mini or args.gather:
             line["gather_ceiling"] = gather_ceiling(torch)
     elif args.compare_cusparse:

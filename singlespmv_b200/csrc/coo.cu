@@ -2,14 +2,16 @@
 // triplet list (the reference aliases the input arrays, opt_coo.cpp:14-19); multiply is y = 0 followed
 // by an `omp atomic` scatter-add per entry (:34-46).
 //
-// B200 multiply: no atomics, no zero-fill pass.  The entry stream is cut into tiles of COO_TILE
-// entries (one CTA each, equal bytes per CTA whatever the row lengths).  A CTA streams row/col/val
-// with 128-bit loads, parks the products and the row ids in shared memory and reduces every run of
-// equal row ids that STARTS in the tile: short runs one thread each, sequentially in storage order
-// with unfused mul/add (bit-identical to opt_crs.cpp:61-67), long runs one warp each (shuffle tree).
-// The thread that finds a run start also zero-fills the empty rows in front of it (beta = 0).  Runs
-// crossing a tile boundary are finished by a second tiny kernel (short: recomputed sequentially;
-// long: per-tile carries added in tile order -> deterministic).
+// B200 multiply: no atomics, no zero-fill pass, two kernels in this file:
+//  * coo_stream_kernel (default, options.coo_path = 0): the "entry stream" -- TMA-fed tiles, per-lane runs in registers,
+//    one segmented warp scan per 128 entries, deterministic stitching of the pieces (described at the kernel);
+//  * coo_tile_kernel (coo_path = 1, and the COO tail of HYB): the order-preserving kernel of round 1.  The entry stream is
+//    cut into tiles of COO_TILE entries (one CTA each).  A CTA streams row/col/val with 128-bit loads, parks the products
+//    and the row ids in shared memory and reduces every run of equal row ids that STARTS in the tile: short runs one thread
+//    each, sequentially in storage order with unfused mul/add (bit-identical to opt_crs.cpp:61-67), long runs one warp each
+//    (shuffle tree).  The thread that finds a run start also zero-fills the empty rows in front of it (beta = 0).  Runs
+//    crossing a tile boundary are finished by a second tiny kernel (short: recomputed sequentially; long: per-tile carries
+//    added in tile order -> deterministic).
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -181,9 +183,11 @@ __global__ void coo_fixup_kernel(const int *__restrict__ row, const int *__restr
 //   * a warp owns CS_CHUNK consecutive entries of the tile, 128 at a time: a lane multiplies 4 consecutive entries,
 //     reduces the runs of equal row ids that start AND end inside them in registers, and one segmented warp scan
 //     (5 shuffle steps) finishes the runs that cross lanes; the open run is carried in a register to the next 128;
-//   * a chunk writes y for every run that STARTS in it (and zero-fills the empty rows in front of each run: beta = 0);
-//     the leading entries that continue a run of an earlier chunk go to carry[chunk], and the fix-up kernel adds the
-//     carries in chunk order (deterministic; no atomics, unlike the reference's `omp atomic`, opt_coo.cpp:34-46).
+//   * a warp writes y for every run that starts AND ends in its chunk (and zero-fills the empty rows in front of each
+//     run: beta = 0); after the tile's barrier one thread stitches the chunks -- the leading piece of a chunk belongs to
+//     the run open at the end of the chunk before it -- and the tile's own leading piece goes to carry[tile]: the fix-up
+//     kernel adds the carries in tile order (deterministic; no atomics, unlike the reference's `omp atomic`,
+//     opt_coo.cpp:34-46).
 // Sums are re-associated across lanes: y is within the 1e-12 tolerance, not bit-identical to the CRS order (the
 // reference's own COO order is not defined either).  options.coo_path = 1 keeps the order-preserving tile kernel.
 constexpr int CS_THREADS = 256;
