@@ -524,6 +524,11 @@ def gather_ceiling(torch):
             mg = cmp.b200cmp_gather(C.c_longlong(tb), C.c_longlong(1 << 29), 2, 5, C.byref(ms))
             if mg > 0:
                 out[name] = {"ggathers_per_s": mg * 1e6 / (ms.value * 1e-3) / 1e9, "ms_per_536M": ms.value * 536.870912 / mg}
+        # the same gathers with a coalesced 12 B/gather stream through the threads' 128-bit loads beside them
+        ms = C.c_float()
+        mg = cmp.b200cmp_gather_stream(C.c_longlong(45 << 20), C.c_longlong(1 << 29), 2, 5, C.byref(ms))
+        if mg > 0:
+            out["table_45MB_plus_12B_stream"] = {"ggathers_per_s": mg * 1e6 / (ms.value * 1e-3) / 1e9, "ms_per_536M": ms.value * 536.870912 / mg}
         return out
     except Exception as e:                                   # noqa: BLE001
         return {"error": repr(e)}

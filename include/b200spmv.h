@@ -91,8 +91,9 @@ typedef struct {
                             fp64 products and sums.  Multiply with b200spmv_multiply_f32 / _host_f32; tolerance 1e-5
                             against the reference's (fp64) CRS result.  Halves the bytes of every array but the indices */
     int hyb_k;           /* HYB: width of the ELL part; 0 = the largest width that max(4096, nRow/3) rows still fill */
-    int coo_path;        /* COO: 0 = entry stream (TMA-fed tiles, segmented warp scans; sums re-associated within 1e-12),
-                            1 = the order-preserving tile kernel (rows <= 64 entries bit-identical to the CRS result) */
+    int coo_path;        /* COO: 0 = entry stream (segmented warp scans; sums re-associated within 1e-12), fed by TMA bulk copies or
+                            by the lanes' own loads, whichever suits the matrix; 1 = the order-preserving tile kernel (rows <= 64
+                            entries bit-identical to the CRS result); 2 / 3 = force the load-fed / the TMA-fed entry stream */
     int reserved[5];
 } b200spmv_options;
 

@@ -83,7 +83,7 @@ struct RowBlocked : Format {
             if (n) shift_rows_kernel<<<ceil_div(n, 256), 256, 0, s>>>(row_d + e[(size_t)g], n, r0, local.p);
             B2_KERNEL_CHECK();
             std::unique_ptr<Format> f(make_format(format, opt));
-            CooView A{r1 - r0, nCol, (int)n, local.p, col_d + e[(size_t)g], val_d + e[(size_t)g]};
+            CooView A{r1 - r0, nCol, (int)n, local.p, col_d + e[(size_t)g], val_d + e[(size_t)g], r0};
             B2_TRY(f->convert(A, s));
             B2_CUDA(cudaStreamSynchronize(s));
             blk.push_back(std::move(f));

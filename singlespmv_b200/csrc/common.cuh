@@ -75,6 +75,7 @@ struct CooView {
     int nnz;                 // < 2^31 like the reference (src/util.h:8)
     const int *row, *col;    // device
     const double *val;       // device
+    int rowOffset = 0;       // global row of local row 0 (row blocks of a larger matrix, blocked.cu): only locality heuristics use it
 };
 
 // how a multiply over a row range treats what y already holds (shared by the tile-stream and the row-chunk stream)
@@ -142,6 +143,9 @@ int exclusive_scan_i64(const long long *in_d, long long *out_d, int n, cudaStrea
 int sum_i32_as_i64(const int *in_d, int n, long long *out_h, cudaStream_t s);
 // min and max of in_d[b..e) (e > b); synchronous
 int minmax_i32(const int *in_d, long long b, long long e, int *mn_h, int *mx_h);
+// largest |col - row| (synchronises); gathers_need_l2: the x entries a stretch of rows touches span more than 32 MB
+int max_band(const int *row_d, const int *col_d, int nnz, int rowOffset, int *band_h, cudaStream_t s);
+bool gathers_need_l2(int band);
 // checks the input contract: sorted by (row, col), no duplicates, indices in range
 int validate_sorted_coo(const CooView &A, cudaStream_t s);
 

@@ -200,7 +200,11 @@ struct CooChunkRec {            // what a warp reports about its chunk; combined
     int pad;
 };
 
-template <int E>
+// TMA = true: persistent CTAs, tiles brought in by bulk copies (above).  TMA = false: one tile per CTA, the lanes load their
+// entries straight from global memory with 128-bit streaming loads -- for matrices whose x gathers depend on L2 residency
+// (R-MAT, uniform random): with bulk copies in flight x does not stay in L2 (profiles/r2_experiments.md), with LDG + evict_first
+// it does.
+template <int E, bool TMA>
 __global__ void __launch_bounds__(CS_THREADS)
 coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, const double *__restrict__ val,
                   const double *__restrict__ x, double *__restrict__ y, double *__restrict__ carry, int nnz, int nRow,
@@ -230,11 +234,13 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
         tma_load_1d(scol + s * E, col + t0, b4, &full[s], pol_stream);
         tma_load_1d(sval + s * E, val + t0, b8, &full[s], pol_stream);
     };
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
-    __syncthreads();
-    if (tid == 0) {
-        if ((int)blockIdx.x < nTiles) issue(0, blockIdx.x);
-        if ((int)(blockIdx.x + gridDim.x) < nTiles) issue(1, blockIdx.x + gridDim.x);
+    if (TMA) {
+        if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+        __syncthreads();
+        if (tid == 0) {
+            if ((int)blockIdx.x < nTiles) issue(0, blockIdx.x);
+            if ((int)(blockIdx.x + gridDim.x) < nTiles) issue(1, blockIdx.x + gridDim.x);
+        }
     }
     // row id in front of a tile (thread 0 keeps it; fetched one tile ahead so that nobody waits for it)
     int tileBefore = -1;
@@ -250,9 +256,9 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
         const int tNext = t + gridDim.x;
         int nextBefore = -1;
         if (tid == 0 && tNext < nTiles) nextBefore = row[(long long)tNext * E - 1];
-        mbar_wait(&full[s], (uint32_t)(k >> 1) & 1u);
-        const int *R = srow + s * E, *Cc = scol + s * E;
-        const double *V = sval + s * E;
+        if (TMA) mbar_wait(&full[s], (uint32_t)(k >> 1) & 1u);
+        const int *R = TMA ? srow + s * E : row + t0, *Cc = TMA ? scol + s * E : col + t0;
+        const double *V = TMA ? sval + s * E : val + t0;
         if (nGroups > 0) {
             int before = tileBefore;
             if (lane == 0 && warp > 0) before = R[c0 - 1];
@@ -268,11 +274,16 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                 int4 r, c;
                 double2 v0, v1;
                 const bool fullGroup = c0 + g * 128 + 128 <= n;
-                if (fullGroup) {
+                if (fullGroup && TMA) {
                     r = *reinterpret_cast<const int4 *>(R + e);
                     c = *reinterpret_cast<const int4 *>(Cc + e);
                     v0 = *reinterpret_cast<const double2 *>(V + e);
                     v1 = *reinterpret_cast<const double2 *>(V + e + 2);
+                } else if (fullGroup) {
+                    r = ld_stream_i4(R + e, pol_stream);
+                    c = ld_stream_i4(Cc + e, pol_stream);
+                    v0 = ld_stream_d2(V + e, pol_stream);
+                    v1 = ld_stream_d2(V + e + 2, pol_stream);
                 } else {                                      // ragged end of the last tile: missing entries repeat the last row with value 0
                     const int last = R[n - 1];
                     r.x = e < n ? R[e] : last; r.y = e + 1 < n ? R[e + 1] : last; r.z = e + 2 < n ? R[e + 2] : last; r.w = e + 3 < n ? R[e + 3] : last;
@@ -368,7 +379,7 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
             if (accRow >= 0) y[accRow] = a2;
             carry[t] = tilePiece;
         }
-        if (tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
+        if (TMA && tid == 0 && t + 2 * (int)gridDim.x < nTiles) issue(s, t + 2 * gridDim.x);
         tileBefore = nextBefore;
     }
 }
@@ -393,9 +404,10 @@ struct CooFormat : Format {
     DevBuf<int> row, col;
     DevBuf<double> val, carry;
     int nTiles = 0;
-    int path = 0;                                             // 0 = entry stream (coo_stream_kernel), 1 = order-preserving tile kernel
+    int path = 0;                                             // 0 = entry stream fed by TMA, 1 = order-preserving tile kernel, 2 = entry stream fed by LDG
     int E = 2048;                                             // entry stream: entries per tile
-    explicit CooFormat(int path_) : path(path_) {}
+    int want = 0;                                             // options.coo_path (0 = choose the feed from the matrix)
+    explicit CooFormat(int path_) : want(path_) {}
 
     int convert(const CooView &A, cudaStream_t s) override
     {
@@ -413,9 +425,20 @@ struct CooFormat : Format {
         B2_CUDA(cudaMemcpyAsync(val.p, A.val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
         static const char *env_path = getenv("B200SPMV_COO_PATH");
         static const int env_e = getenv("B200SPMV_COO_E") ? atoi(getenv("B200SPMV_COO_E")) : 0;
-        if (env_path) path = strcmp(env_path, "tile") == 0 ? 1 : 0;
-        // tiles of 1024 entries (6 CTAs per SM) against 2048 (3 per SM): profiles/r2_experiments.md
-        E = env_e == 2048 ? 2048 : 1024;
+        path = want;
+        if (env_path) path = strcmp(env_path, "tile") == 0 ? 1 : strcmp(env_path, "ldg") == 0 ? 2 : strcmp(env_path, "tma") == 0 ? 3 : 0;
+        if (path == 0 || path == 3) {
+            // Entry stream: who feeds it?  Banded matrices (stencils: the x entries a tile touches are a few MB that L1 / L2 hold
+            // whatever else streams by) take the TMA-fed persistent kernel: c5 607 GFLOP/s against 530 with loads.  Matrices whose
+            // gathers range over tens of MB live on x staying in L2, which it does not with bulk copies in flight: c3 (R-MAT) 211
+            // GFLOP/s TMA-fed against 410 with the lanes' own evict-first loads (profiles/r2_experiments.md).
+            int band = 0;
+            if (path == 0) B2_TRY(max_band(A.row, A.col, nnz, A.rowOffset, &band, s));
+            path = (path == 0 && gathers_need_l2(band)) ? 2 : 0;
+        }
+        // tiles of 1024 entries (TMA-fed: 6 CTAs per SM against 3 with 2048; c5 0.85 against 0.74 of the roofline); load-fed: a
+        // warp's 256 consecutive entries of a 2048 tile (c3 410 against 385 GFLOP/s)
+        E = env_e == 2048 || env_e == 1024 ? env_e : (path == 2 ? 2048 : 1024);
         nTiles = ceil_div(nnz, path == 1 ? COO_TILE : E);
         B2_TRY(carry.alloc((size_t)nTiles));
         B2_CUDA(cudaStreamSynchronize(s));
@@ -429,7 +452,8 @@ struct CooFormat : Format {
             B2_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * (size_t)nRow, s));
             return B200SPMV_OK;
         }
-        if (path != 1) return E == 1024 ? stream_multiply<1024>(x, y, s) : stream_multiply<2048>(x, y, s);
+        if (path == 2) return E == 1024 ? stream_multiply<1024, false>(x, y, s) : stream_multiply<2048, false>(x, y, s);
+        if (path != 1) return E == 1024 ? stream_multiply<1024, true>(x, y, s) : stream_multiply<2048, true>(x, y, s);
         coo_tile_kernel<false><<<nTiles, COO_THREADS, 0, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, 1);
         B2_KERNEL_CHECK();
         if (nTiles > 1) {
@@ -439,10 +463,10 @@ struct CooFormat : Format {
         return B200SPMV_OK;
     }
 
-    template <int TE> int stream_multiply(const double *x, double *y, cudaStream_t s)
+    template <int TE, bool TMA> int stream_multiply(const double *x, double *y, cudaStream_t s)
     {
-        constexpr size_t smem = 32 * (size_t)TE;
-        auto kern = coo_stream_kernel<TE>;
+        constexpr size_t smem = TMA ? 32 * (size_t)TE : 0;
+        auto kern = coo_stream_kernel<TE, TMA>;
         static std::map<int, int> per_sm;                      // resident CTAs per SM of this instantiation, by device
         static int sms = 0;
         static const int env_b = getenv("B200SPMV_COO_CTAS") ? atoi(getenv("B200SPMV_COO_CTAS")) : 0;
@@ -458,7 +482,7 @@ struct CooFormat : Format {
             it = per_sm.emplace(dev, n).first;
         }
         const int perSm = env_b > 0 ? std::min(env_b, it->second) : std::min(it->second, 6);
-        const int grid = std::min(nTiles, sms * perSm);
+        const int grid = TMA ? std::min(nTiles, sms * perSm) : nTiles;
         kern<<<grid, CS_THREADS, smem, s>>>(row.p, col.p, val.p, x, y, carry.p, nnz, nRow, nTiles);
         B2_KERNEL_CHECK();
         if (nTiles > 1) {

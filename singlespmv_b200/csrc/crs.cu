@@ -145,8 +145,12 @@ struct CrsFormat : Format {
         B2_TRY(cs.build(ptr.p, idx.p, f32 ? (const void *)val32.p : (const void *)val.p, f32, nRow, nnz, maxLen, s));
         // path: 1 = tile-stream always; 2 = round 1's row-block stream where it applies (longest row <= 16);
         // otherwise the TMA-fed row-chunk stream when the rows are short enough, else the tile-stream
+        // ... unless the gathers range over tens of MB (uniform random, R-MAT): x must stay in L2, which it does with the
+        // tile-stream's evict-first loads and does not with bulk copies in flight (uniform 2^24 x 11: 40 G entries/s TMA-fed)
         use_rbs = path_opt == 2 && !prec && rowblock_applies(maxLen, nnz);
-        short_rows = path_opt != 1 && (use_rbs || cs.ok);
+        int band = 0;
+        if (path_opt == 0 && cs.ok) B2_TRY(max_band(A.row, A.col, nnz, A.rowOffset, &band, s));
+        short_rows = path_opt != 1 && (use_rbs || (cs.ok && !gathers_need_l2(band)));
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }

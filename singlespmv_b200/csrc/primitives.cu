@@ -162,6 +162,33 @@ int minmax_i32(const int *in_d, long long b, long long e, int *mn_h, int *mx_h)
     return B200SPMV_OK;
 }
 
+// largest |col - row| of a COO: how far apart the x entries of neighbouring rows lie.  Matrices whose gathers range over
+// tens of MB depend on x staying in L2, which it does not while TMA bulk copies stream the matrix (profiles/r2_experiments.md):
+// the formats use this to choose between their TMA-fed and their load-fed kernels.
+__global__ void band_kernel(const int *__restrict__ row, const int *__restrict__ col, int nnz, int rowOffset, int *__restrict__ out)
+{
+    int m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, abs(col[i] - (row[i] + rowOffset)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+int max_band(const int *row_d, const int *col_d, int nnz, int rowOffset, int *band_h, cudaStream_t s)
+{
+    *band_h = 0;
+    if (nnz <= 0) return B200SPMV_OK;
+    DevBuf<int> b;
+    B2_TRY(b.alloc(1));
+    B2_CUDA(cudaMemsetAsync(b.p, 0, sizeof(int), s));
+    band_kernel<<<std::min(ceil_div(nnz, 256), 4096), 256, 0, s>>>(row_d, col_d, nnz, rowOffset, b.p);
+    B2_KERNEL_CHECK();
+    B2_CUDA(cudaMemcpyAsync(band_h, b.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return B200SPMV_OK;
+}
+bool gathers_need_l2(int band) { return 8LL * band > (32LL << 20); }
+
 // ---------------------------------------------------------------- input contract
 __global__ void validate_kernel(const int *__restrict__ row, const int *__restrict__ col, int nnz,
                                 int nRow, int nCol, int *bad)

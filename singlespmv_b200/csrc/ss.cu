@@ -296,7 +296,9 @@ struct SsFormat : Format {
         B2_TRY(max_row_length(row_ptr.p, nRow, &maxLen, s));
         B2_TRY(cs.build(row_ptr.p, col2d.p, val2d.p, false, nRow, nnz, maxLen, s));
         use_rbs = path_opt == 2 && rowblock_applies(maxLen, nnz);
-        short_rows = path_opt != 1 && (use_rbs || cs.ok);
+        int band = 0;
+        if (path_opt == 0 && cs.ok) B2_TRY(max_band(A.row, A.col, nnz, A.rowOffset, &band, s));
+        short_rows = path_opt != 1 && (use_rbs || (cs.ok && !gathers_need_l2(band)));   // see crs.cu
         cb.reset();
         if (!faithful) B2_TRY(make_col_block_engine(A, row_ptr.p, cbs_want, s, &cb));
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));

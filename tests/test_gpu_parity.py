@@ -237,8 +237,12 @@ def test_coo(sp, oracle, all_cases):
         assert np.array_equal(A_opt.array("col_idx", np.int32), col), name
         assert np.array_equal(A_opt.array("val", np.float64), val), name
         assert A_opt.scalar("alg_bytes") == 16 * len(row) + 8 * nCol + 8 * nRow
-        assert A_opt.scalar("coo_path") == 0
+        assert A_opt.scalar("coo_path") in (0, 2)                                # entry stream, TMA- or load-fed
         assert_y(y, y_ref, row, col, val, x, nRow)
+        for forced in (2, 3):
+            A_f, y_f = run_host(sp, "coo", nRow, nCol, row, col, val, x, coo_path=forced)
+            assert A_f.scalar("coo_path") == (2 if forced == 2 else 0)
+            assert_y(y_f, y_ref, row, col, val, x, nRow)
         # coo_path = 1: the order-preserving tile kernel
         A_opt, y = run_host(sp, "coo", nRow, nCol, row, col, val, x, coo_path=1)
         assert A_opt.scalar("coo_path") == 1
@@ -284,10 +288,11 @@ def test_coo_entry_stream_chunk_boundaries(sp, oracle):
         val = rng.standard_normal(len(row))
         x = rng.random(nCol)
         y_ref = oracle.crs_result(nRow, row, col, val, x)
-        _, y = run_host(sp, "coo", nRow, nCol, row, col, val, x)
-        assert_y(y, y_ref, row, col, val, x, nRow)
-        empty = np.array(lens) == 0
-        assert np.all(y[empty] == 0.0)
+        for path in (2, 3):                                  # load-fed and TMA-fed entry stream
+            _, y = run_host(sp, "coo", nRow, nCol, row, col, val, x, coo_path=path)
+            assert_y(y, y_ref, row, col, val, x, nRow)
+            empty = np.array(lens) == 0
+            assert np.all(y[empty] == 0.0)
 
 
 # ------------------------------------------------------------------------------------------ JDS
@@ -926,7 +931,7 @@ def test_ell_dense_row_never_reads_past_x(sp):
         assert np.array_equal(lcol[2], np.arange(nCol))                   # empty row: padding col = k (opt_ell.cpp:48)
 
 
-GUARD_FORMATS = [("crs", {}), ("crs", {"crs_path": 1}), ("coo", {}), ("coo", {"coo_path": 1}), ("ell", {}), ("jds", {}), ("dia", {}),
+GUARD_FORMATS = [("crs", {}), ("crs", {"crs_path": 1}), ("coo", {"coo_path": 3}), ("coo", {"coo_path": 2}), ("coo", {"coo_path": 1}), ("ell", {}), ("jds", {}), ("dia", {}),
                  ("ss", {}), ("css", {"n_block": 3}), ("csr5", {}), ("hyb", {}), ("ell", {"col_blocks": 3}), ("jds", {"col_blocks": 2})]
 
 
