@@ -68,9 +68,9 @@ try:                                    # captures of this round's kernels, writ
             NCU_TRAFFIC[tuple(_k.split("/"))] = _v
 except Exception:
     pass
-DOMINANT = {"crs": "crs_tma_kernel (longest row <= 16) / tile_stream_kernel", "ss": "crs_tma_kernel / tile_stream_kernel",
-            "css": "tile_stream_kernel (one launch per column block)", "ell": "ell_spmv_kernel / cbs_spmv_kernel (column-blocked)",
-            "jds": "jds_spmv_kernel / cbs_spmv_kernel (column-blocked)", "dia": "dia_spmv_tma_kernel", "coo": "coo_stream_kernel",
+DOMINANT = {"crs": "chunk_stream_kernel (longest row <= 16) / tile_stream_kernel", "ss": "chunk_stream_kernel / tile_stream_kernel / ell_spmv_kernel per column block",
+            "css": "tile_stream_kernel (one launch per column block)", "ell": "ell_spmv_kernel (gather-bound matrices: one launch per column block)",
+            "jds": "jds_spmv_kernel / ell_spmv_kernel per column block (gather-bound matrices)", "dia": "dia_spmv_tma_kernel", "coo": "coo_stream_kernel",
             "csr5": "c5_compute_kernel", "hyb": "ell_spmv_kernel + coo_tile_kernel"}
 
 

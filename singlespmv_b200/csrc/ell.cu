@@ -9,24 +9,27 @@
 namespace b2 {
 
 // groups[s] = ceil(max row length in slice s / V)
+// Row r holds the entries [beg[r], end[r]) of col / val: the whole row (beg = ptr, end = ptr + 1) or its part inside one
+// column block (EllColBlocks below).
 template <int V>
-__global__ void ell_slice_groups_kernel(const int *__restrict__ ptr, int nRow, int nSlices,
+__global__ void ell_slice_groups_kernel(const int *__restrict__ beg, const int *__restrict__ end, int nRow, int nSlices,
                                         long long *__restrict__ groups)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s > nSlices) return;                       // s == nSlices: sentinel entry for the scan
     const int r = s * 32 + lane;
-    int len = (s < nSlices && r < nRow) ? ptr[r + 1] - ptr[r] : 0;
+    int len = (s < nSlices && r < nRow) ? end[r] - beg[r] : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
     if (lane == 0) groups[s] = (len + V - 1) / V;
 }
 
+// padCol: column of the slots beyond K (0 for the format's own layout; the first column of the block for a column block)
 template <int V, typename VT>
-__global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restrict__ col,
+__global__ void ell_fill_kernel(const int *__restrict__ beg, const int *__restrict__ end, const int *__restrict__ col,
                                 const double *__restrict__ val, int nRow, int nSlices,
-                                const long long *__restrict__ slice_off, int K, int *__restrict__ ecol,
+                                const long long *__restrict__ slice_off, int K, int padCol, int *__restrict__ ecol,
                                 VT *__restrict__ eval)
 {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -34,7 +37,7 @@ __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restri
     if (s >= nSlices) return;
     const int r = s * 32 + lane;
     const long long g0 = slice_off[s], g1 = slice_off[s + 1];
-    const int b = r < nRow ? ptr[r] : 0, len = r < nRow ? ptr[r + 1] - b : 0;
+    const int b = r < nRow ? beg[r] : 0, len = r < nRow ? end[r] - b : 0;
     for (long long g = g0; g < g1; g++)
 #pragma unroll
         for (int j = 0; j < V; j++) {
@@ -43,7 +46,7 @@ __global__ void ell_fill_kernel(const int *__restrict__ ptr, const int *__restri
             const bool real = k < len;
             // padding: col = slot index (opt_ell.cpp:48) for the reference's K slots; the extra slots that round a
             // slice up to V (k >= K, never exported) point at column 0 so that no gather leaves x when K is close to nCol
-            ecol[at] = real ? col[b + k] : ((r < nRow && k < K) ? k : 0);
+            ecol[at] = real ? col[b + k] : ((r < nRow && k < K) ? k : padCol);
             eval[at] = real ? (VT)val[b + k] : (VT)0;      // fp32 storage: rounded to nearest once, here
         }
 }
@@ -107,7 +110,8 @@ __device__ __forceinline__ double ell_gather(const double *p, uint64_t pol, int 
 }
 __device__ __forceinline__ float ell_gather(const float *p, uint64_t pol, int) { return ld_x(p, pol); }
 
-template <int V, int XM, typename VT, typename XT, typename AT>
+// ACC: the row sums CONTINUE what y holds (acc = y[r]; ...; y[r] = acc): the next column block of the same running sum.
+template <int V, int XM, typename VT, typename XT, typename AT, bool ACC = false>
 __global__ void __launch_bounds__(256)
 ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
                 const VT *__restrict__ eval, const XT *__restrict__ x, XT *__restrict__ y,
@@ -118,7 +122,9 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
     if (s >= sliceEnd) return;
     const uint64_t pol_stream = policy_evict_first(), pol_x = policy_evict_last();
     const long long g0 = slice_off[s], g1 = slice_off[s + 1];
-    AT acc = (AT)0;
+    const int r = s * 32 + lane;
+    const bool mine = r >= rowBegin && r < rowEnd;
+    AT acc = (ACC && mine) ? (AT)y[r] : (AT)0;
     long long g = g0;
     for (; g + 2 <= g1; g += 2) {
         EllGroup<V, VT> a, b;
@@ -143,8 +149,7 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
 #pragma unroll
         for (int j = 0; j < V; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)xa[j], (AT)a.v[j]));
     }
-    const int r = s * 32 + lane;
-    if (r >= rowBegin && r < rowEnd) y[r] = (XT)acc;
+    if (mine) y[r] = (XT)acc;
 }
 
 // Logical [nRow][K] view for parity checks (slots beyond the slice width are padding).
@@ -185,7 +190,7 @@ struct EllFormat : Format {
         DevBuf<long long> groups;
         B2_TRY(groups.alloc((size_t)nSlices + 1));
         B2_TRY(slice_off.alloc((size_t)nSlices + 1));
-        ell_slice_groups_kernel<VV><<<ceil_div(((long long)nSlices + 1) * 32, 256), 256, 0, s>>>(ptr, nRow, nSlices, groups.p);
+        ell_slice_groups_kernel<VV><<<ceil_div(((long long)nSlices + 1) * 32, 256), 256, 0, s>>>(ptr, ptr + 1, nRow, nSlices, groups.p);
         B2_KERNEL_CHECK();
         B2_TRY(exclusive_scan_i64(groups.p, slice_off.p, nSlices + 1, s));
         long long totalGroups = 0;
@@ -196,8 +201,8 @@ struct EllFormat : Format {
         else B2_TRY(eval.alloc((size_t)slots));
         if (nSlices) {
             const int grid = ceil_div((long long)nSlices * 32, 256);
-            if (prec) ell_fill_kernel<VV, float><<<grid, 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices, slice_off.p, K, ecol.p, eval32.p);
-            else ell_fill_kernel<VV, double><<<grid, 256, 0, s>>>(ptr, A.col, A.val, nRow, nSlices, slice_off.p, K, ecol.p, eval.p);
+            if (prec) ell_fill_kernel<VV, float><<<grid, 256, 0, s>>>(ptr, ptr + 1, A.col, A.val, nRow, nSlices, slice_off.p, K, 0, ecol.p, eval32.p);
+            else ell_fill_kernel<VV, double><<<grid, 256, 0, s>>>(ptr, ptr + 1, A.col, A.val, nRow, nSlices, slice_off.p, K, 0, ecol.p, eval.p);
             B2_KERNEL_CHECK();
         }
         return B200SPMV_OK;
@@ -285,6 +290,7 @@ struct EllFormat : Format {
         }
         if (n == "launches") { *out = (cb != nullptr) ? cb->n_blocks() : 1; return true; }
         if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
+        if (n == "col_block_engine") { *out = (cb == nullptr) ? 0 : (cb->name()[0] == 'e' ? 1 : 2); return true; }   // 1 = sliced ELL per block, 2 = tile-stream
         if (n == "precision") { *out = prec; return true; }
         return false;
     }
@@ -310,5 +316,105 @@ struct EllFormat : Format {
 };
 
 Format *make_ell(const b200spmv_options &o) { return new EllFormat(o); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Column-block engine as one sliced ELL per column block (colblocks.cuh).  A row's columns ascend, so its entries inside
+// column block b are a contiguous piece [start_b[r], start_b+1[r]) of the row: every block gets its own slices of 32 rows,
+// padded to the longest piece INSIDE the block (V = 2 slots at a time), and is multiplied by the ELL kernel -- one lane per
+// row, ascending slots, block b continuing the sum block b-1 left in y.  Same bits as the format's own kernel and as the
+// reference CRS result, whatever the row lengths.  On config 2 the pieces are Binomial(32, 1/3): 1.58 slots per entry;
+// the padding costs stream bytes but no gather wavefronts (a padded lane re-reads one hot x entry), and the gathers are
+// what bounds the kernel: 2.25 ms against 2.94 ms for the tile-stream per block (profiles/r2_experiments.md).
+__global__ void cb_starts_kernel(const int *__restrict__ ptr, const int *__restrict__ col, int nRow, int B, int nb,
+                                 int *__restrict__ start /* [nb + 1][nRow] */)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRow) return;
+    const int b0 = ptr[r], e0 = ptr[r + 1];
+    int at = b0;
+    for (int b = 0; b <= nb; b++) {
+        const long long bound = (long long)b * B;              // first column of block b
+        while (at < e0 && col[at] < bound) at++;
+        start[(size_t)b * nRow + r] = b == nb ? e0 : at;
+    }
+}
+
+struct EllColBlocks : ColBlockEngine {
+    struct Blk {
+        DevBuf<long long> slice_off;
+        DevBuf<int> ecol;
+        DevBuf<double> eval;
+        long long slots = 0;
+    };
+    int nRow = 0, nSlices = 0;
+    std::vector<std::unique_ptr<Blk>> blk;
+    long long slots = 0;
+
+    int build(const CooView &A, const int *row_ptr, int nb, double maxRatio, bool *ok, cudaStream_t s)
+    {
+        *ok = false;
+        nRow = A.nRow;
+        nSlices = ceil_div(nRow, 32);
+        const int B = (A.nCol + nb - 1) / nb;
+        DevBuf<int> start;
+        DevBuf<long long> groups;
+        B2_TRY(start.alloc((size_t)(nb + 1) * nRow));
+        B2_TRY(groups.alloc((size_t)nSlices + 1));
+        cb_starts_kernel<<<ceil_div(nRow, 256), 256, 0, s>>>(row_ptr, A.col, nRow, B, nb, start.p);
+        B2_KERNEL_CHECK();
+        slots = 0;
+        for (int b = 0; b < nb; b++) {
+            std::unique_ptr<Blk> k(new Blk());
+            const int *beg = start.p + (size_t)b * nRow, *end = start.p + (size_t)(b + 1) * nRow;
+            B2_TRY(k->slice_off.alloc((size_t)nSlices + 1));
+            ell_slice_groups_kernel<2><<<ceil_div(((long long)nSlices + 1) * 32, 256), 256, 0, s>>>(beg, end, nRow, nSlices, groups.p);
+            B2_KERNEL_CHECK();
+            B2_TRY(exclusive_scan_i64(groups.p, k->slice_off.p, nSlices + 1, s));
+            long long totalGroups = 0;
+            B2_CUDA(cudaMemcpyAsync(&totalGroups, k->slice_off.p + nSlices, sizeof(long long), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(cudaStreamSynchronize(s));
+            k->slots = totalGroups * 32 * 2;
+            slots += k->slots;
+            if ((double)slots > maxRatio * (double)std::max(A.nnz, 1)) return B200SPMV_OK;      // too much padding: not this engine
+            B2_TRY(k->ecol.alloc((size_t)k->slots));
+            B2_TRY(k->eval.alloc((size_t)k->slots));
+            if (nSlices) {
+                ell_fill_kernel<2, double><<<ceil_div((long long)nSlices * 32, 256), 256, 0, s>>>(beg, end, A.col, A.val, nRow, nSlices, k->slice_off.p, 0,
+                                                                                                 (int)std::min<long long>((long long)b * B, A.nCol - 1), k->ecol.p, k->eval.p);
+                B2_KERNEL_CHECK();
+            }
+            blk.push_back(std::move(k));
+        }
+        B2_CUDA(cudaStreamSynchronize(s));
+        *ok = true;
+        return B200SPMV_OK;
+    }
+
+    int run(const double *x, double *y, int rb, int re, cudaStream_t s) override
+    {
+        if (rb >= re) return B200SPMV_OK;
+        const int sb = rb / 32, se = ceil_div(re, 32);
+        const int blocks = ceil_div((long long)(se - sb) * 32, 256);
+        for (size_t b = 0; b < blk.size(); b++) {
+            const Blk &k = *blk[b];
+            if (b == 0) ell_spmv_kernel<2, 0, double, double, double, false><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
+            else ell_spmv_kernel<2, 0, double, double, double, true><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
+            B2_KERNEL_CHECK();
+        }
+        return B200SPMV_OK;
+    }
+    int n_blocks() const override { return (int)blk.size(); }
+    const char *name() const override { return "ell"; }
+};
+
+int make_ell_col_blocks(const CooView &A, const int *row_ptr, int nb, double maxRatio, cudaStream_t s,
+                        std::unique_ptr<ColBlockEngine> *out)
+{
+    std::unique_ptr<EllColBlocks> e(new EllColBlocks());
+    bool ok = false;
+    B2_TRY(e->build(A, row_ptr, nb, maxRatio, &ok, s));
+    if (ok) *out = std::move(e);
+    return B200SPMV_OK;
+}
 
 }  // namespace b2

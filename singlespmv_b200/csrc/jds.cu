@@ -238,6 +238,7 @@ struct JdsFormat : Format {
         }
         if (n == "launches") { *out = (cb != nullptr) ? cb->n_blocks() : (nLong > 0) + (nRow > nLong); return true; }
         if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
+        if (n == "col_block_engine") { *out = (cb == nullptr) ? 0 : (cb->name()[0] == 'e' ? 1 : 2); return true; }   // 1 = sliced ELL per block, 2 = tile-stream
         return false;
     }
 

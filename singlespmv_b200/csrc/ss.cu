@@ -351,6 +351,7 @@ struct SsFormat : Format {
     {
         if (prof.scalar(n, out)) return true;
         if (n == "col_blocks") { *out = (cb != nullptr) ? cb->n_blocks() : 0; return true; }
+        if (n == "col_block_engine") { *out = (cb == nullptr) ? 0 : (cb->name()[0] == 'e' ? 1 : 2); return true; }   // 1 = sliced ELL per block, 2 = tile-stream
         if (n == "H") { *out = H; return true; }
         if (n == "nStep") { *out = nStep; return true; }
         if (n == "W") { *out = W; return true; }
@@ -730,6 +731,11 @@ int make_col_block_engine(const CooView &A, const int *row_ptr, int want, cudaSt
         B2_CUDA(cudaStreamSynchronize(s));
         // rows that each live in one block (stencils, banded matrices) already reuse x through L1 / L2
         if ((double)st[0] < 1.5 * (double)st[1]) return B200SPMV_OK;
+    }
+    const char *env_e = getenv("B200SPMV_COL_BLOCK_ENGINE");            // "crs" forces the tile-stream engine (tests, experiments)
+    if (!(env_e && !strcmp(env_e, "crs"))) {
+        B2_TRY(make_ell_col_blocks(A, row_ptr, nb, 2.0, s, out));
+        if (*out) return B200SPMV_OK;
     }
     b200spmv_options o{};
     o.segment_width = 1;

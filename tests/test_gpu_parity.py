@@ -779,7 +779,7 @@ def test_full_size_uniform_and_rmat(sp, oracle):
         for f in fmts:
             m = sp.SpMatOpt(f, **opts.get(f, {})).convert_device(d)
             if kind == "uniform" and f in ("ell", "jds", "ss"):
-                assert m.scalar("col_blocks") == 3, f                    # the gather-bound layout is what runs
+                assert m.scalar("col_blocks") == 3 and m.scalar("col_block_engine") == 1, f   # the gather-bound layout is what runs
             y = _mult(m, x, n)[:rows].cpu().numpy()
             m.destroy()
             err = np.abs(y - y_ref)
@@ -1081,6 +1081,29 @@ def test_column_blocked_layout_bit_exact(sp, oracle, fmt):
             assert A_opt.scalar("alg_bytes") == base_opt.scalar("alg_bytes")
         auto_opt, _ = run_host(sp, fmt, nRow, nCol, row, col, val, x)
         assert auto_opt.scalar("col_blocks") == 0             # x fits in L2: the decision leaves small matrices alone
+
+
+@pytest.mark.parametrize("fmt", ["ell", "jds", "ss"])
+def test_column_block_engines(sp, oracle, fmt, monkeypatch):
+    """The two column-block engines (colblocks.cuh): one sliced ELL per column block (default while the padding stays below
+    two slots per entry) and the tile-stream per block.  Both continue every row's sum from block to block: same bits."""
+    nr, nc, row, col, val = oracle.uniform(5, 6000, 6000, 32)
+    x = oracle.reference_vectors(nc, nr)[0]
+    y_ref = oracle.crs_result(nr, row, col, val, x)
+    monkeypatch.delenv("B200SPMV_COL_BLOCK_ENGINE", raising=False)
+    A1, y1 = run_host(sp, fmt, nr, nc, row, col, val, x, col_blocks=3)
+    assert A1.scalar("col_block_engine") == 1 and A1.scalar("col_blocks") == 3
+    monkeypatch.setenv("B200SPMV_COL_BLOCK_ENGINE", "crs")
+    A2, y2 = run_host(sp, fmt, nr, nc, row, col, val, x, col_blocks=3)
+    monkeypatch.delenv("B200SPMV_COL_BLOCK_ENGINE", raising=False)
+    assert A2.scalar("col_block_engine") == 2
+    assert np.array_equal(y1, y_ref) and np.array_equal(y2, y_ref)
+    # a skewed matrix would need far more than two slots per entry: the tile-stream engine takes it
+    nr, nc, row, col, val = oracle.rmat(42, 12, 120000)
+    x = oracle.reference_vectors(nc, nr)[0]
+    A3, y3 = run_host(sp, fmt, nr, nc, row, col, val, x, col_blocks=2)
+    assert A3.scalar("col_block_engine") == 2
+    assert_y(y3, oracle.crs_result(nr, row, col, val, x), row, col, val, x, nr)
 
 
 def test_column_blocked_long_rows_within_tolerance(sp, oracle, all_cases):
