@@ -28,6 +28,7 @@ constexpr int COLBLOCK_MAX = 32;
 struct ColBlockEngine {
     virtual ~ColBlockEngine() {}
     virtual int run(const double *x, double *y, int rb, int re, cudaStream_t s) = 0;
+    virtual int run_block(int, const double *, double *, int, int, cudaStream_t) { return B200SPMV_ERR_UNSUPPORTED; }   // one block only
     virtual int n_blocks() const = 0;
     virtual const char *name() const = 0;
 };
@@ -38,7 +39,8 @@ struct ColBlockEngine {
 int make_col_block_engine(const CooView &A, const int *row_ptr, int want, cudaStream_t s,
                           std::unique_ptr<ColBlockEngine> *out);
 // one sliced ELL per column block (ell.cu); *out stays empty when the blocks would need more than maxRatio slots per entry
-int make_ell_col_blocks(const CooView &A, const int *row_ptr, int nb, double maxRatio, cudaStream_t s,
+// B: block width (0 = ceil(nCol / nb)); later: what the blocks after the first do with y (CS_CONTINUE, or CS_ADD for CSS)
+int make_ell_col_blocks(const CooView &A, const int *row_ptr, int nb, int B, int later, double maxRatio, cudaStream_t s,
                         std::unique_ptr<ColBlockEngine> *out);
 
 }  // namespace b2

@@ -110,8 +110,9 @@ __device__ __forceinline__ double ell_gather(const double *p, uint64_t pol, int 
 }
 __device__ __forceinline__ float ell_gather(const float *p, uint64_t pol, int) { return ld_x(p, pol); }
 
-// ACC: the row sums CONTINUE what y holds (acc = y[r]; ...; y[r] = acc): the next column block of the same running sum.
-template <int V, int XM, typename VT, typename XT, typename AT, bool ACC = false>
+// ACC = CS_CONTINUE: the row sums continue what y holds (acc = y[r]; ...; y[r] = acc): the next column block of the same
+// running sum.  ACC = CS_ADD: y[r] = y[r] + sum (CSS adds its block sums, src/opt_css.cpp:298).
+template <int V, int XM, typename VT, typename XT, typename AT, int ACC = CS_OVERWRITE>
 __global__ void __launch_bounds__(256)
 ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__ ecol,
                 const VT *__restrict__ eval, const XT *__restrict__ x, XT *__restrict__ y,
@@ -124,7 +125,8 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
     const long long g0 = slice_off[s], g1 = slice_off[s + 1];
     const int r = s * 32 + lane;
     const bool mine = r >= rowBegin && r < rowEnd;
-    AT acc = (ACC && mine) ? (AT)y[r] : (AT)0;
+    const AT y0 = (ACC != CS_OVERWRITE && mine) ? (AT)y[r] : (AT)0;
+    AT acc = ACC == CS_CONTINUE ? y0 : (AT)0;
     long long g = g0;
     for (; g + 2 <= g1; g += 2) {
         EllGroup<V, VT> a, b;
@@ -149,7 +151,7 @@ ell_spmv_kernel(const long long *__restrict__ slice_off, const int *__restrict__
 #pragma unroll
         for (int j = 0; j < V; j++) acc = Arith<AT>::add(acc, Arith<AT>::mul((AT)xa[j], (AT)a.v[j]));
     }
-    if (mine) y[r] = (XT)acc;
+    if (mine) y[r] = (XT)(ACC == CS_ADD ? Arith<AT>::add(y0, acc) : acc);
 }
 
 // Logical [nRow][K] view for parity checks (slots beyond the slice width are padding).
@@ -350,12 +352,14 @@ struct EllColBlocks : ColBlockEngine {
     std::vector<std::unique_ptr<Blk>> blk;
     long long slots = 0;
 
-    int build(const CooView &A, const int *row_ptr, int nb, double maxRatio, bool *ok, cudaStream_t s)
+    int later = CS_CONTINUE;                                  // what blocks after the first do with y: CS_CONTINUE or CS_ADD (CSS)
+
+    int build(const CooView &A, const int *row_ptr, int nb, int Bwant, double maxRatio, bool *ok, cudaStream_t s)
     {
         *ok = false;
         nRow = A.nRow;
         nSlices = ceil_div(nRow, 32);
-        const int B = (A.nCol + nb - 1) / nb;
+        const int B = Bwant > 0 ? Bwant : (A.nCol + nb - 1) / nb;
         DevBuf<int> start;
         DevBuf<long long> groups;
         B2_TRY(start.alloc((size_t)(nb + 1) * nRow));
@@ -390,29 +394,34 @@ struct EllColBlocks : ColBlockEngine {
         return B200SPMV_OK;
     }
 
-    int run(const double *x, double *y, int rb, int re, cudaStream_t s) override
+    int run_block(int b, const double *x, double *y, int rb, int re, cudaStream_t s) override
     {
         if (rb >= re) return B200SPMV_OK;
         const int sb = rb / 32, se = ceil_div(re, 32);
         const int blocks = ceil_div((long long)(se - sb) * 32, 256);
-        for (size_t b = 0; b < blk.size(); b++) {
-            const Blk &k = *blk[b];
-            if (b == 0) ell_spmv_kernel<2, 0, double, double, double, false><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
-            else ell_spmv_kernel<2, 0, double, double, double, true><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
-            B2_KERNEL_CHECK();
-        }
+        const Blk &k = *blk[(size_t)b];
+        if (b == 0) ell_spmv_kernel<2, 0, double, double, double, CS_OVERWRITE><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
+        else if (later == CS_ADD) ell_spmv_kernel<2, 0, double, double, double, CS_ADD><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
+        else ell_spmv_kernel<2, 0, double, double, double, CS_CONTINUE><<<blocks, 256, 0, s>>>(k.slice_off.p, k.ecol.p, k.eval.p, x, y, rb, re, sb, se);
+        B2_KERNEL_CHECK();
+        return B200SPMV_OK;
+    }
+    int run(const double *x, double *y, int rb, int re, cudaStream_t s) override
+    {
+        for (size_t b = 0; b < blk.size(); b++) B2_TRY(run_block((int)b, x, y, rb, re, s));
         return B200SPMV_OK;
     }
     int n_blocks() const override { return (int)blk.size(); }
     const char *name() const override { return "ell"; }
 };
 
-int make_ell_col_blocks(const CooView &A, const int *row_ptr, int nb, double maxRatio, cudaStream_t s,
+int make_ell_col_blocks(const CooView &A, const int *row_ptr, int nb, int B, int later, double maxRatio, cudaStream_t s,
                         std::unique_ptr<ColBlockEngine> *out)
 {
     std::unique_ptr<EllColBlocks> e(new EllColBlocks());
+    e->later = later;
     bool ok = false;
-    B2_TRY(e->build(A, row_ptr, nb, maxRatio, &ok, s));
+    B2_TRY(e->build(A, row_ptr, nb, B, maxRatio, &ok, s));
     if (ok) *out = std::move(e);
     return B200SPMV_OK;
 }

@@ -470,6 +470,7 @@ struct CssFormat : Format {
     DevBuf<int> row_ptr, row2d, col2d, seg_index;      // row_ptr: [nBlock][nRow+1]
     DevBuf<double> val2d, val_buf;
     std::vector<std::unique_ptr<CssBlock>> blocks;
+    std::unique_ptr<ColBlockEngine> ellb;   // gather-bound matrices: the blocks as sliced ELL (multiply only; the CSS arrays stay)
     PhaseTimer prof;
 
     explicit CssFormat(const b200spmv_options &o) : W(o.segment_width), nBlockWanted(o.n_block), faithful(o.ss_faithful) { prof.on = o.profile != 0 && o.ss_faithful != 0; }
@@ -563,6 +564,11 @@ struct CssFormat : Format {
             B2_CUDA(cudaMemcpyAsync(st, stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
             B2_CUDA(cudaStreamSynchronize(s));
             gather_bound = (double)st[0] >= 1.5 * (double)st[1];
+            // gather-bound: one sliced ELL per column block, block sums ADDED like the tile-stream path does (colblocks.cuh)
+            const char *env_e = getenv("B200SPMV_COL_BLOCK_ENGINE");
+            ellb.reset();
+            if (gather_bound && !faithful && !(env_e && !strcmp(env_e, "crs")))
+                B2_TRY(make_ell_col_blocks(A, ptr.p, nBlock, B, CS_ADD, 2.0, s, &ellb));
         }
         if (faithful) B2_TRY(val_buf.alloc((size_t)slots));
         B2_CUDA(cudaStreamSynchronize(s));
@@ -577,6 +583,7 @@ struct CssFormat : Format {
             return B200SPMV_OK;
         }
         if (!faithful) {
+            if (ellb) return ellb->run(x, y, 0, nRow, s);
             for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->run(x, y, 0, nRow, gather_bound, b > 0 ? CS_ADD : CS_OVERWRITE, s));
             return B200SPMV_OK;
         }
@@ -615,6 +622,7 @@ struct CssFormat : Format {
             B2_CUDA(cudaMemsetAsync(y + rb, 0, sizeof(double) * (size_t)(re - rb), s));
             return B200SPMV_OK;
         }
+        if (ellb) return ellb->run(x, y, rb, re, s);
         for (int b = 0; b < nBlock; b++) B2_TRY(blocks[(size_t)b]->run(x, y, rb, re, gather_bound, b > 0 ? CS_ADD : CS_OVERWRITE, s));
         return B200SPMV_OK;
     }
@@ -642,6 +650,7 @@ struct CssFormat : Format {
     int multiply_rows_slice(int i, int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (faithful || nBlock < 1) return multiply_rows(rb, re, x, y, s);
+        if (ellb) return ellb->run_block(i, x, y, rb, re, s);
         return blocks[(size_t)i]->run(x, y, rb, re, gather_bound, i > 0 ? CS_ADD : CS_OVERWRITE, s);
     }
 
@@ -649,6 +658,7 @@ struct CssFormat : Format {
     {
         if (prof.scalar(n, out)) return true;
         if (n == "B") { *out = B; return true; }
+        if (n == "col_block_engine") { *out = ellb ? 1 : (gather_bound ? 2 : 0); return true; }
         if (n == "nBlock") { *out = nBlock; return true; }
         if (n == "totalH") { *out = totalH; return true; }
         if (n == "W") { *out = W; return true; }
@@ -658,7 +668,8 @@ struct CssFormat : Format {
         }
         if (n == "launches") {
             long long l = 0;
-            if (!faithful) for (auto &k : blocks) l += k->cs.ok ? 1 : (k->ts.nTiles > 1 ? 2 : 1);
+            if (!faithful && ellb) l = ellb->n_blocks();
+            else if (!faithful) for (auto &k : blocks) l += k->cs.ok ? 1 : (k->ts.nTiles > 1 ? 2 : 1);
             else { l = 2; for (auto &k : blocks) { l += 1; for (int c : k->counts) l += c > 0; } }
             *out = l;
             return true;
@@ -734,7 +745,7 @@ int make_col_block_engine(const CooView &A, const int *row_ptr, int want, cudaSt
     }
     const char *env_e = getenv("B200SPMV_COL_BLOCK_ENGINE");            // "crs" forces the tile-stream engine (tests, experiments)
     if (!(env_e && !strcmp(env_e, "crs"))) {
-        B2_TRY(make_ell_col_blocks(A, row_ptr, nb, 2.0, s, out));
+        B2_TRY(make_ell_col_blocks(A, row_ptr, nb, 0, CS_CONTINUE, 2.0, s, out));
         if (*out) return B200SPMV_OK;
     }
     b200spmv_options o{};

@@ -1098,6 +1098,16 @@ def test_column_block_engines(sp, oracle, fmt, monkeypatch):
     monkeypatch.delenv("B200SPMV_COL_BLOCK_ENGINE", raising=False)
     assert A2.scalar("col_block_engine") == 2
     assert np.array_equal(y1, y_ref) and np.array_equal(y2, y_ref)
+    if fmt == "ss":
+        # CSS itself on a gather-bound matrix: the same ELL blocks with the block sums ADDED (src/opt_css.cpp:298): same
+        # association as its tile-stream path, within the tolerance of the CRS order
+        C1, z1 = run_host(sp, "css", nr, nc, row, col, val, x, n_block=3, segment_width=4)
+        assert C1.scalar("col_block_engine") == 1
+        monkeypatch.setenv("B200SPMV_COL_BLOCK_ENGINE", "crs")
+        C2, z2 = run_host(sp, "css", nr, nc, row, col, val, x, n_block=3, segment_width=4)
+        monkeypatch.delenv("B200SPMV_COL_BLOCK_ENGINE", raising=False)
+        assert C2.scalar("col_block_engine") == 2 and np.array_equal(z1, z2)
+        assert_y(z1, y_ref, row, col, val, x, nr)
     # a skewed matrix would need far more than two slots per entry: the tile-stream engine takes it
     nr, nc, row, col, val = oracle.rmat(42, 12, 120000)
     x = oracle.reference_vectors(nc, nr)[0]
