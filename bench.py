@@ -59,7 +59,7 @@ HEADLINE = "c5"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE multiply's launches of the dominant kernel, from the committed
 # ncu --set full captures (profiles/r1_ncu_kernels.md, profiles/r2_ncu_kernels.md).  Keyed by (workload, format); else null.
-NCU_TRAFFIC = {("c2", "css"): 3 * 2415011680, ("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
+NCU_TRAFFIC = {("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
                ("c4", "dia"): 3870562096, ("c4", "ell"): 5853024560, ("c5", "dia"): 9634725000,
                ("c5", "csr5"): 13638726000}
 try:                                    # captures of this round's kernels, written by scripts/ncu_traffic.py
