@@ -266,7 +266,7 @@ B200SPMV_API int b200spmv_xwin_plan(b200spmv_xwin *w, const int *halo_cols_h, in
                        const long long *bounds_h, const int *readers_h, int nReaders);
 /* one step's exchange, asynchronous on `stream` (may be captured in a CUDA graph); every rank calls it once per step */
 B200SPMV_API int b200spmv_xwin_exchange(b200spmv_xwin *w, void *stream);
-/* steps finished; *timed_out != 0 if a flag wait ever gave up after ~2 s (a peer that did not take part) */
+/* steps finished; *timed_out != 0 if a flag wait ever gave up after ~10 s (a peer that did not take part) */
 B200SPMV_API int b200spmv_xwin_status(b200spmv_xwin *w, long long *steps, int *timed_out);
 B200SPMV_API int b200spmv_xwin_free(b200spmv_xwin *w);
 

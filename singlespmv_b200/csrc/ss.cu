@@ -481,6 +481,8 @@ struct CssFormat : Format {
         nRow = A.nRow; nCol = A.nCol; nnz = A.nnz;
         if (!input_checked) B2_TRY(validate_sorted_coo(A, s));
         blocks.clear();
+        ellb.reset();
+        gather_bound = lean ? gather_bound : false;
         B = nCol > 0 ? (nCol + nBlockWanted - 1) / nBlockWanted : 1;       // ceil(nCol / N_BLOCK), opt_css.cpp:34
         if (B < 1) B = 1;
         nBlock = nCol / B + (nCol % B ? 1 : 0);                            // opt_css.cpp:35
@@ -566,7 +568,6 @@ struct CssFormat : Format {
             gather_bound = (double)st[0] >= 1.5 * (double)st[1];
             // gather-bound: one sliced ELL per column block, block sums ADDED like the tile-stream path does (colblocks.cuh)
             const char *env_e = getenv("B200SPMV_COL_BLOCK_ENGINE");
-            ellb.reset();
             if (gather_bound && !faithful && !(env_e && !strcmp(env_e, "crs")))
                 B2_TRY(make_ell_col_blocks(A, ptr.p, nBlock, B, CS_ADD, 2.0, s, &ellb));
         }

@@ -21,7 +21,7 @@ namespace {
 constexpr int XW_MAXPEERS = 64;
 constexpr size_t XW_HEADER = 4096;                 // flag words in front of x_ext (same allocation = one IPC handle)
 constexpr int XW_THREADS = 64;                     // small CTAs: they must fit into what the interior rows' persistent CTAs leave of an SM
-constexpr long long XW_SPIN_LIMIT = 4000000000LL;  // ~2 s of SM clocks: a rank that never shows up ends the kernel with an error flag
+constexpr long long XW_SPIN_LIMIT = 20000000000LL; // ~10 s of SM clocks: a rank that never shows up ends the kernel with an error flag
 
 struct XwHeader {                                  // lives at the start of every window
     unsigned long long ready[XW_MAXPEERS];         // ready[p] = last step for which rank p's owned slice is in place

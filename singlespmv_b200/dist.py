@@ -348,6 +348,14 @@ class DistSpmv:
             for w in (dist.batch_isend_irecv(ops) if ops else []):
                 w.wait()                                     # comm stream waits for NCCL's stream
 
+    def exchange_status(self):
+        """(steps finished, timed_out) of the x-window exchange; (None, False) on the NCCL path.  Synchronises."""
+        if self.exchange != "peer" or not self.block.win:
+            return None, False
+        steps, bad = C.c_longlong(), C.c_int()
+        check(lib.b200spmv_xwin_status(self.block.win, C.byref(steps), C.byref(bad)))
+        return int(steps.value), bool(bad.value)
+
     def _step_eager(self):
         """the exchange on the comm stream, interior rows on the current stream meanwhile, boundary rows once the halo
         has landed."""
@@ -641,6 +649,8 @@ def run_partitioned_bench(args, wl, wl_key):
     clocks = sampler.stop() if rank == 0 else None
     launches = torch.tensor([b.launches_per_step()], dtype=torch.int64, device="cuda")
     dist.all_reduce(launches)
+    bad = torch.tensor([1 if eng.exchange_status()[1] else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(bad)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -654,6 +664,7 @@ def run_partitioned_bench(args, wl, wl_key):
                                              "(CUDA IPC) by one exchange kernel per rank" if eng.exchange == "peer" else
                                              "over NCCL send/recv"),
                            "exchange": eng.exchange, "exchange_fallback_reason": eng.exchange_error,
+                           "exchange_flag_timeouts": int(bad.item()),
                            "local_kernel": ("crs_tma_kernel (row-chunk stream)" if fmt == "crs" and b.A.scalar("short_row_path") else
                                             "tile_stream_kernel" if fmt in ("crs", "ss", "css") else fmt),
                            "launch": ("one CUDA graph per step (both streams captured)" if graphed else "eager launches") + "; the faster of the two, timed at plan time",
