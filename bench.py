@@ -59,7 +59,7 @@ HEADLINE = "c5"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE multiply's launches of the dominant kernel, from the committed
 # ncu --set full captures (profiles/r1_ncu_kernels.md, profiles/r2_ncu_kernels.md).  Keyed by (workload, format); else null.
-NCU_TRAFFIC = {("c3", "crs"): 3308867896, ("c3", "csr5"): 3383375304,
+NCU_TRAFFIC = {("c3", "csr5"): 3383375304,
                ("c4", "dia"): 3870562096, ("c4", "ell"): 5853024560, ("c5", "dia"): 9634725000,
                ("c5", "csr5"): 13638726000}
 try:                                    # captures of this round's kernels, written by scripts/ncu_traffic.py
@@ -68,7 +68,7 @@ try:                                    # captures of this round's kernels, writ
             NCU_TRAFFIC[tuple(_k.split("/"))] = _v
 except Exception:
     pass
-DOMINANT = {"crs": "chunk_stream_kernel (longest row <= 16) / tile_stream_kernel", "ss": "chunk_stream_kernel / tile_stream_kernel / ell_spmv_kernel per column block",
+DOMINANT = {"crs": "chunk_stream_kernel (longest row <= 16, banded) / entry_stream_kernel (gather-bound) / tile_stream_kernel", "ss": "chunk_stream_kernel / tile_stream_kernel / ell_spmv_kernel per column block",
             "css": "tile_stream_kernel (one launch per column block)", "ell": "ell_spmv_kernel (gather-bound matrices: one launch per column block)",
             "jds": "jds_spmv_kernel / ell_spmv_kernel per column block (gather-bound matrices)", "dia": "dia_spmv_tma_kernel", "coo": "coo_stream_kernel",
             "csr5": "c5_compute_kernel", "hyb": "ell_spmv_kernel + coo_tile_kernel"}

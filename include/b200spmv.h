@@ -75,9 +75,11 @@ typedef struct {
                             operation order (src/opt_ss.cpp:222-303); 0 = fused one-pass kernel */
     int value_f32;       /* CRS: 1 = store the matrix values as fp32 (rounded once at conversion); x, y and all
                             arithmetic stay fp64.  8 instead of 12 B/nnz; tolerance 1e-5 (BASELINE.json north star) */
-    int crs_path;        /* CRS / SS: 0 = choose from the longest row (<= 16: TMA-fed row-chunk stream, else tile-stream),
-                            1 = always the tile-stream kernel; when the short-row path applies: 2 = the warp-per-32-rows
-                            row-block stream of round 1, 3 = the TMA-fed row-chunk stream */
+    int crs_path;        /* CRS / SS: 0 = choose from the matrix (longest row <= 16 and banded: TMA-fed row-chunk stream; CRS on matrices
+                            whose gathers range over > 32 MB of x: the entry stream, sums re-associated within 1e-12; else the
+                            tile-stream), 1 = always the tile-stream kernel (rows of up to 64 entries summed in the reference's
+                            order); when the short-row path applies: 2 = the warp-per-32-rows row-block stream of round 1, 3 = the
+                            TMA-fed row-chunk stream; CRS: 4 = always the entry stream */
     int profile;         /* SS/CSS with ss_faithful: time the Mul and the Sum phase of every multiply with CUDA events
                             (the reference's -DPROFILING, src/util.h:59-65); the multiply then synchronises and the
                             scalars MulTime_ns / SumTime_ns hold the last call's phases */

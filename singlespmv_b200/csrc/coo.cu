@@ -326,10 +326,25 @@ coo_stream_kernel(const int *__restrict__ row, const int *__restrict__ col, cons
                 const unsigned below = m & (0xffffffffu >> (31 - lane));           // starts at or below this lane
                 const int seg = below ? 31 - __clz(below) : 0;
                 double v = acc;
+                // a segment of k lanes needs the steps d < k only: find the longest gap between starts (with a virtual start at
+                // lane 0) from the warp-uniform mask -- 7-entry rows (c5) need ONE step, 27-entry rows (c4) three
+                unsigned cov = m | 1u;
+                cov |= cov << 1;
+                int steps = 1;
+                if (cov != 0xffffffffu) {
+                    cov |= cov << 2; steps = 2;
+                    if (cov != 0xffffffffu) {
+                        cov |= cov << 4; steps = 3;
+                        if (cov != 0xffffffffu) { cov |= cov << 8; steps = cov != 0xffffffffu ? 5 : 4; }
+                    }
+                }
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const double u = __shfl_up_sync(0xffffffffu, v, d);
-                    if (lane - d >= seg) v = __dadd_rn(v, u);
+                for (int i = 0; i < 5; i++) {
+                    if (i < steps) {
+                        const int d = 1 << i;
+                        const double u = __shfl_up_sync(0xffffffffu, v, d);
+                        if (lane - d >= seg) v = __dadd_rn(v, u);
+                    }
                 }
                 if (!below) v = __dadd_rn(v, cin);                                  // still the run that was open when the group began
                 double excl = __shfl_up_sync(0xffffffffu, v, 1);

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "chunk_stream.cuh"
+#include "entry_stream.cuh"
 #include "tile_stream.cuh"
 
 namespace b2 {
@@ -118,6 +119,8 @@ struct CrsFormat : Format {
     bool f32;
     TileStream ts;
     ChunkStream cs;
+    EntryStream es;
+    bool use_es = false;
     int path_opt;
     int prec;                             // options.precision: 0 fp64 vectors, 1 fp32 vectors + sums, 2 fp32 vectors, fp64 sums
     explicit CrsFormat(const b200spmv_options &o) : f32(o.value_f32 != 0 || o.precision != 0), path_opt(o.crs_path), prec(o.precision) {}
@@ -149,8 +152,18 @@ struct CrsFormat : Format {
         // tile-stream's evict-first loads and does not with bulk copies in flight (uniform 2^24 x 11: 40 G entries/s TMA-fed)
         use_rbs = path_opt == 2 && !prec && rowblock_applies(maxLen, nnz);
         int band = 0;
-        if (path_opt == 0 && cs.ok) B2_TRY(max_band(A.row, A.col, nnz, A.rowOffset, &band, s));
-        short_rows = path_opt != 1 && (use_rbs || (cs.ok && !gathers_need_l2(band)));
+        if (path_opt == 0 || path_opt == 4) B2_TRY(max_band(A.row, A.col, nnz, A.rowOffset, &band, s));
+        short_rows = path_opt != 1 && path_opt != 4 && (use_rbs || (cs.ok && !gathers_need_l2(band)));
+        // gather-bound matrices (fp64): the load-fed entry stream (entry_stream.cuh) -- c3 441 GFLOP/s against 365 for the tile-stream
+        // (cuSPARSE CSR: 405).  Banded matrices with medium rows keep the tile-stream: the TMA-fed entry stream is level with it
+        // (c4: 659 against 642) and the tile-stream sums rows of up to 64 entries in the reference's order.  crs_path = 4 forces the
+        // entry stream, crs_path = 1 / B200SPMV_CRS_PATH=tile the tile-stream.
+        static const char *force = getenv("B200SPMV_CRS_PATH");
+        use_es = false;
+        if (!short_rows && !f32 && !prec && (path_opt == 4 || (path_opt == 0 && gathers_need_l2(band))) && !(force && !strcmp(force, "tile"))) {
+            B2_TRY(es.build(ptr.p, idx.p, val.p, nRow, nnz, gathers_need_l2(band), s));
+            use_es = es.ok;
+        }
         B2_CUDA(cudaStreamSynchronize(s));
         return B200SPMV_OK;
     }
@@ -166,6 +179,7 @@ struct CrsFormat : Format {
     int multiply_rows(int rb, int re, const double *x, double *y, cudaStream_t s) override
     {
         if (prec) { set_error("multiply: the handle was created with precision = %d, use b200spmv_multiply_f32", prec); return B200SPMV_ERR_STATE; }
+        if (!short_rows && use_es) return es.run_rows(x, y, rb, re, s);
         if (!short_rows) return ts.run_rows(x, y, CS_OVERWRITE, rb, re, s);
         if (rb < 0 || re > nRow || rb > re) { set_error("multiply_rows: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
         if (rb == re) return B200SPMV_OK;
@@ -173,7 +187,7 @@ struct CrsFormat : Format {
         return cs.run(x, y, rb, re, CS_OVERWRITE, s);
     }
     bool has_rows() const override { return true; }
-    int prepare_rows(int rb, int re) override { return short_rows ? B200SPMV_OK : ts.prepare(rb, re); }
+    int prepare_rows(int rb, int re) override { return short_rows ? B200SPMV_OK : use_es ? es.prepare(rb, re) : ts.prepare(rb, re); }
     int col_extent(int rb, int re, int *cmin, int *cmax) override
     {
         if (rb < 0 || re > nRow || rb > re) { set_error("col_extent: bad row range [%d,%d)", rb, re); return B200SPMV_ERR_INVALID; }
@@ -190,7 +204,8 @@ struct CrsFormat : Format {
             *out = (f32 ? 8LL : 12LL) * nnz + 4LL * (nRow + 1) + (prec ? 4LL : 8LL) * ((long long)nCol + nRow);
             return true;
         }
-        if (n == "launches") { *out = short_rows ? 1 : (ts.nTiles > 1 ? 2 : 1); return true; }
+        if (n == "launches") { *out = short_rows ? 1 : use_es ? (es.nTiles > 1 ? 2 : 1) + (es.nEmpty ? 1 : 0) : (ts.nTiles > 1 ? 2 : 1); return true; }
+        if (n == "crs_kernel") { *out = short_rows ? 1 : use_es ? (es.tma ? 2 : 3) : 0; return true; }   // 0 tile-stream, 1 row-chunk stream, 2 / 3 entry stream (TMA- / load-fed)
         if (n == "maxLength") { *out = maxLen; return true; }
         if (n == "short_row_path") { *out = short_rows ? 1 : 0; return true; }
         if (n == "nTiles") { *out = ts.nTiles; return true; }

@@ -158,6 +158,37 @@ def test_host_multiply_pipeline_large(sp, oracle, fmt, opt):
             assert np.array_equal(y2, y2_ref)
 
 
+def test_crs_entry_stream(sp, oracle, all_cases):
+    """crs_path = 4: the entry stream (entry_stream.cuh; the default on gather-bound matrices such as config 3) -- row starts as a
+    bit per entry instead of row_ptr, segmented warp scans; within the tolerance for every case incl. empty rows, one long row,
+    rows ending on every lane / group / chunk / tile boundary; row ranges leave the other rows alone."""
+    import torch
+    rng = np.random.default_rng(17)
+    extra = []
+    for lens in ([4] * 64 + [128] * 3 + [256, 256, 1, 255, 2048, 2047, 1, 1, 4096 + 256, 3], [1] * 5000,
+                 [0, 0, 3, 0, 125, 0, 0, 128, 1, 0, 255, 257, 0, 0, 0, 6000, 0, 2, 0, 0], [27] * 700 + [0] * 9, [1, 2047, 2048 * 5, 1]):
+        nRow, nCol = len(lens), 12000
+        row = np.repeat(np.arange(nRow), lens).astype(np.int32)
+        col = np.concatenate([np.sort(rng.choice(nCol, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int32)
+        extra.append(("lens", nRow, nCol, row, col, rng.standard_normal(len(row)), rng.random(nCol)))
+    for name, nRow, nCol, row, col, val, x in list(all_cases) + extra:
+        y_ref = oracle.crs_result(nRow, row, col, val, x)
+        A_opt, y = run_host(sp, "crs", nRow, nCol, row, col, val, x, crs_path=4)
+        if len(row):
+            assert A_opt.scalar("crs_kernel") == 2, name                  # small matrices are banded enough: TMA-fed
+        assert_y(y, y_ref, row, col, val, x, nRow)
+        if nRow > 40:
+            xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            yd = torch.full((nRow,), -3.0, dtype=torch.float64, device="cuda")
+            lo, hi = nRow // 5, nRow - nRow // 3
+            A_opt.prepare_rows(lo, hi)
+            A_opt.multiply_rows(lo, hi, xd.data_ptr(), yd.data_ptr())
+            torch.cuda.synchronize()
+            yy = yd.cpu().numpy()
+            assert np.all(yy[:lo] == -3.0) and np.all(yy[hi:] == -3.0), name
+            assert np.array_equal(yy[lo:hi], y[lo:hi]), name               # deterministic: same bits as the whole multiply
+
+
 def test_crs_paths_agree(sp, oracle):
     """Short-row matrices take the row-block stream by default; crs_path=1 forces the tile-stream.  Both sum every
     row in the reference's order -> identical y, and both equal the reference CRS result bit for bit."""
@@ -784,7 +815,7 @@ def test_full_size_uniform_and_rmat(sp, oracle):
             m.destroy()
             err = np.abs(y - y_ref)
             assert np.all((err <= 1e-12 * np.abs(y_ref)) | (err <= 1e-12 * mag)), (kind, f, float(err.max()))
-            if f in ("ell", "jds", "ss", "crs"):
+            if f in ("ell", "jds", "ss"):                                   # (crs on R-MAT: the entry stream, sums re-associated)
                 short = lens <= 64
                 assert np.array_equal(y[short], y_ref[short]), (kind, f)
         d.free()
@@ -847,9 +878,10 @@ def test_more_than_int32_entries_on_one_gpu(sp):
     from singlespmv_b200.dist import _DevArray
     vals = torch.as_tensor(_DevArray(d.c.val_d, d.nNnz), device="cuda").view(n, 40)
     acc = torch.zeros(n, dtype=torch.float64, device="cuda")
-    for k in range(40):                                        # ascending column order, like the kernel
+    for k in range(40):                                        # ascending column order
         acc += vals[:, k]
-    assert torch.equal(y1, acc)
+    assert m.scalar("crs_kernel") == 3                         # gather-bound: the load-fed entry stream (sums re-associated)
+    assert torch.allclose(y1, acc, rtol=1e-13, atol=0.0)
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
     y = _mult(m, x, n)
@@ -931,7 +963,7 @@ def test_ell_dense_row_never_reads_past_x(sp):
         assert np.array_equal(lcol[2], np.arange(nCol))                   # empty row: padding col = k (opt_ell.cpp:48)
 
 
-GUARD_FORMATS = [("crs", {}), ("crs", {"crs_path": 1}), ("coo", {"coo_path": 3}), ("coo", {"coo_path": 2}), ("coo", {"coo_path": 1}), ("ell", {}), ("jds", {}), ("dia", {}),
+GUARD_FORMATS = [("crs", {}), ("crs", {"crs_path": 1}), ("crs", {"crs_path": 4}), ("coo", {"coo_path": 3}), ("coo", {"coo_path": 2}), ("coo", {"coo_path": 1}), ("ell", {}), ("jds", {}), ("dia", {}),
                  ("ss", {}), ("css", {"n_block": 3}), ("csr5", {}), ("hyb", {}), ("ell", {"col_blocks": 3}), ("jds", {"col_blocks": 2})]
 
 
