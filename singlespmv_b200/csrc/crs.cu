@@ -160,7 +160,8 @@ struct CrsFormat : Format {
         // entry stream, crs_path = 1 / B200SPMV_CRS_PATH=tile the tile-stream.
         static const char *force = getenv("B200SPMV_CRS_PATH");
         use_es = false;
-        if (!short_rows && !f32 && !prec && (path_opt == 4 || (path_opt == 0 && gathers_need_l2(band))) && !(force && !strcmp(force, "tile"))) {
+        const bool force_es = force && !strcmp(force, "es") && path_opt == 0;          // experiments: entry stream wherever the rows are not short
+        if (!short_rows && !f32 && !prec && (path_opt == 4 || force_es || (path_opt == 0 && gathers_need_l2(band))) && !(force && !strcmp(force, "tile"))) {
             B2_TRY(es.build(ptr.p, idx.p, val.p, nRow, nnz, gathers_need_l2(band), s));
             use_es = es.ok;
         }
