@@ -25,14 +25,29 @@ using namespace b2;
 
 namespace {
 
-// x_ext halo slot i <- the owner's x slice: slots [0, nLeft) sit below the owned slice, the rest above it
-__global__ void mg_pull_kernel(const double *const *__restrict__ peer_x, const int *__restrict__ owner,
-                               const int *__restrict__ idx, int nHalo, int nLeft, int nLocal, double *__restrict__ x_ext)
+// x_ext halo slot i <- the owner's x slice: slots [0, nLeft) sit below the owned slice, the rest above it.
+// CTAs of 64 threads in a grid-stride loop with four loads in flight: the interior rows run as persistent CTAs that leave ~4096
+// registers per SM, so only small CTAs get an SM while they run (measured on the torchrun twin of this kernel, xwin.cu: 256-thread
+// CTAs only started once the interior rows had drained)
+constexpr int MG_PULL_THREADS = 64;
+__global__ void __launch_bounds__(MG_PULL_THREADS)
+mg_pull_kernel(const double *const *__restrict__ peer_x, const int *__restrict__ owner, const int *__restrict__ idx, int nHalo,
+               int nLeft, int nLocal, double *__restrict__ x_ext)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nHalo) return;
-    const double v = peer_x[owner[i]][idx[i]];                 // NVLink peer load (or a local load when owner == self)
-    x_ext[i < nLeft ? i : nLocal + i] = v;
+    const int stride = gridDim.x * MG_PULL_THREADS;
+    for (int i0 = blockIdx.x * MG_PULL_THREADS + threadIdx.x; i0 < nHalo; i0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * stride;
+            if (i < nHalo) v[u] = peer_x[owner[i]][idx[i]];        // NVLink peer load (or a local load when owner == self)
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * stride;
+            if (i < nHalo) x_ext[i < nLeft ? i : nLocal + i] = v[u];
+        }
+    }
 }
 
 struct MgBlock {
@@ -173,7 +188,10 @@ static int mg_enqueue_step(b200spmv_mg *m, bool captured)
             for (auto &p : m->blk) if (p.dev != b.dev) MG_CUDA(cudaStreamWaitEvent(b.comm, p.ev_x, 0));   // the owners' slices are in place
         }
         if (nHalo) {
-            mg_pull_kernel<<<ceil_div(nHalo, 256), 256, 0, b.comm>>>(b.peer_x, b.pull_owner, b.pull_idx, nHalo, b.nLeft, b.nLocal, b.x_ext);
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b.dev);
+            mg_pull_kernel<<<std::max(1, std::min(2 * sms, ceil_div(nHalo, 4 * MG_PULL_THREADS))), MG_PULL_THREADS, 0, b.comm>>>(
+                b.peer_x, b.pull_owner, b.pull_idx, nHalo, b.nLeft, b.nLocal, b.x_ext);
             B2_KERNEL_CHECK();
         }
         MG_CUDA(cudaEventRecord(captured ? b.cev_halo : b.ev_halo, b.comm));
