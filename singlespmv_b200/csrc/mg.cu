@@ -17,6 +17,7 @@
 //               events): a step is a single cudaGraphLaunch from the single host thread
 // The multi-process twin of this file is singlespmv_b200/dist.py (torchrun, one process per GPU, NCCL send/recv).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -406,6 +407,27 @@ int b200spmv_mg_upload_x(b200spmv_mg *m, const double *x_h)
     return B200SPMV_OK;
 }
 
+static int mg_sync_all(b200spmv_mg *m)
+{
+    for (auto &b : m->blk) {
+        B2_CUDA(cudaSetDevice(b.dev));
+        B2_CUDA(cudaStreamSynchronize(b.compute));
+        B2_CUDA(cudaStreamSynchronize(b.comm));
+    }
+    return B200SPMV_OK;
+}
+
+// one step, by graph launch or by eager launches
+static int mg_step(b200spmv_mg *m, bool graph)
+{
+    if (graph) {
+        B2_CUDA(cudaSetDevice(m->blk[0].dev));
+        B2_CUDA(cudaGraphLaunch(m->graph, m->blk[0].compute));
+        return B200SPMV_OK;
+    }
+    return mg_enqueue_step(m, false);
+}
+
 int b200spmv_mg_multiply(b200spmv_mg *m)
 {
     B2_TRY(mg_ready(m, "mg_multiply"));
@@ -414,14 +436,27 @@ int b200spmv_mg_multiply(b200spmv_mg *m)
         B2_TRY(mg_enqueue_step(m, false));                     // one eager step first: lazy kernel loading, first-use attributes
         for (auto &b : m->blk) { B2_CUDA(cudaSetDevice(b.dev)); B2_CUDA(cudaDeviceSynchronize()); }
         B2_TRY(mg_capture(m));
+        if (m->graph) {
+            // graph replay or eager launches, whichever is faster here (plan time, like DistSpmv.choose_launch): the multi-device
+            // graph saves the host ~50 API calls per step but its fork / join nodes add latency -- 8 GPUs, c5: 0.320 ms replayed
+            // against 0.291 ms eager; B200SPMV_MG_GRAPH=1 / B200SPMV_MG_NO_GRAPH keep one of them unconditionally
+            static const bool keep = getenv("B200SPMV_MG_GRAPH") != nullptr;
+            double t[2] = {0.0, 0.0};
+            for (int mode = 0; mode < 2 && !keep; mode++) {
+                for (int i = 0; i < 3; i++) B2_TRY(mg_step(m, mode == 0));
+                B2_TRY(mg_sync_all(m));
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int i = 0; i < 10; i++) B2_TRY(mg_step(m, mode == 0));
+                B2_TRY(mg_sync_all(m));
+                t[mode] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            }
+            if (!keep && t[1] < t[0]) {
+                cudaGraphExecDestroy(m->graph);
+                m->graph = nullptr;
+            }
+        }
     }
-    int st = B200SPMV_OK;
-    if (m->graph) {
-        B2_CUDA(cudaSetDevice(m->blk[0].dev));
-        B2_CUDA(cudaGraphLaunch(m->graph, m->blk[0].compute));
-    } else {
-        st = mg_enqueue_step(m, false);
-    }
+    const int st = mg_step(m, m->graph != nullptr);
     B2_CUDA(cudaSetDevice(m->home));
     return st;
 }
