@@ -64,6 +64,23 @@ def test_no_cpu_fallback():
         sp.DeviceCoo("lap2d5", 8)
 
 
+def test_multi_gpu_entry_points_need_a_device():
+    """The multi-GPU entry points (single-process handle, x windows) refuse to work without CUDA devices and validate their
+    arguments on the host."""
+    import singlespmv_b200 as sp
+    from singlespmv_b200._lib import lib
+    h = C.c_void_p()
+    assert lib.b200spmv_xwin_create(0, 0, 10, 0, C.byref(h)) == -1            # world < 1
+    assert lib.b200spmv_xwin_create(3, 2, 10, 0, C.byref(h)) == -1            # rank outside the world
+    assert lib.b200spmv_xwin_create(0, 2, 10, 11, C.byref(h)) == -1           # owned slice outside x_ext
+    assert lib.b200spmv_xwin_exchange(None, None) < 0 and lib.b200spmv_xwin_free(None) == 0
+    if sp.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    assert lib.b200spmv_xwin_create(0, 2, 10, 0, C.byref(h)) == -2 and not h.value
+    m = C.c_void_p()
+    assert lib.b200spmv_mg_create(2, 0, None, C.byref(m)) == -2 and b"no CPU fallback" in lib.b200spmv_last_error()
+
+
 def test_product_does_not_touch_the_oracle():
     """oracle/ is test infrastructure: nothing under singlespmv_b200/ or include/ may reference it."""
     bad = []
